@@ -1,0 +1,144 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs.  Bars (BASELINE.json north_star): hit counts and coordinates bit-exact,
+qs/gs/Rec within 1e-5 absolute, GT identical, GQ within 1e-3."""
+import numpy as np
+import pytest
+
+from oracle import batch_oracle as BO
+from oracle import vapor_oracle as O
+from vapor_b200 import synth
+from vapor_b200.engine import Batch, MODE_ABS, MODE_ABS_AND_W10, MODE_REDEF, MODE_W10
+
+pytestmark = pytest.mark.gpu
+
+QS_TOL = 1e-5     # north_star: VaPoR_qs/gs/Rec within 1e-5 absolute
+GQ_TOL = 1e-3     # north_star: VaPoR_GQ within 1e-3
+
+
+def _compare(res, exp, exact_scores=True):
+    np.testing.assert_array_equal(res.task_hits, exp["task_hits"])
+    np.testing.assert_array_equal(res.task_hitsum, exp["task_hitsum"])
+    np.testing.assert_array_equal(res.task_status, exp["task_status"])
+    if exact_scores:      # all statistics are exact integer sums + one IEEE division: bit-equal in practice
+        np.testing.assert_array_equal(res.task_stat, exp["task_stat"])
+        np.testing.assert_array_equal(res.task_score, exp["task_score"])
+    else:
+        np.testing.assert_allclose(res.task_score, exp["task_score"], rtol=0, atol=QS_TOL)
+    np.testing.assert_array_equal(res.sv_nscore, exp["sv_nscore"])
+    np.testing.assert_array_equal(res.sv_gt, exp["sv_gt"])
+    np.testing.assert_allclose(res.sv_qs, exp["sv_qs"], rtol=0, atol=QS_TOL)
+    np.testing.assert_allclose(res.sv_gs, exp["sv_gs"], rtol=0, atol=QS_TOL)
+    np.testing.assert_allclose(res.sv_gq, exp["sv_gq"], rtol=0, atol=GQ_TOL)
+
+
+def test_dotdata_bit_exact(engine):
+    rng = np.random.default_rng(11)
+    for k in (4, 10, 16, 20, 30, 40):
+        ref = synth.random_dna(rng, 1500)
+        reads, off = synth.simulate_reads(rng, ref, np.array([0]), np.array([1400]), np.array([1200]))
+        got = engine.dotdata(k, reads, ref)
+        exp = O.dotdata(k, reads.tobytes().decode(), ref.tobytes().decode())
+        np.testing.assert_array_equal(got, exp)
+
+
+def test_dotdata_palindromes_and_revcomp(engine):
+    # ACGT is its own reverse complement: the reference emits those dots twice
+    read, ref = "ACGTACGTAA", "ACGTTTACGT"
+    got = engine.dotdata(4, read, ref)
+    exp = O.dotdata(4, read, ref)
+    np.testing.assert_array_equal(got, exp)
+    assert (got[0] == got[1]).all()
+    rng = np.random.default_rng(3)
+    s = synth.random_dna(rng, 800)
+    rc = synth.revcomp(s)
+    for k in (10, 20):
+        np.testing.assert_array_equal(engine.dotdata(k, rc, s), O.dotdata(k, rc.tobytes().decode(), s.tobytes().decode()))
+
+
+def test_dotdata_alphabet_edge_cases(engine):
+    rng = np.random.default_rng(4)
+    s = synth.random_dna(rng, 600).copy()
+    r = s.copy()
+    s[100:140] = ord("N"); r[100:140] = ord("N")          # N k-mers match each other
+    s[200:260] += 32                                        # lower-case structure never matches upper-case read
+    s[300:320] = ord("X")                                   # X never matches
+    s[400] = ord("R"); r[400] = ord("Y")                    # IUPAC -> N on both sides
+    r[500:520] += 32; s[500:520] += 32                      # lower == lower
+    for k in (10, 20):
+        np.testing.assert_array_equal(engine.dotdata(k, r, s), O.dotdata(k, r.tobytes().decode(), s.tobytes().decode()))
+    with pytest.raises(KeyError):
+        bad = r.copy(); bad[50] = ord("X")
+        engine.dotdata(10, bad, s)
+
+
+def test_dotdata_short_and_empty(engine):
+    assert len(engine.dotdata(10, "ACGT", "ACGTACGTACGTACGT")) == 0
+    assert len(engine.dotdata(10, "ACGTACGTACGTACGT", "ACG")) == 0
+    assert len(engine.dotdata(10, "", "")) == 0
+
+
+def test_dotdata_repetitive_overflow(engine):
+    # poly-A x poly-A: every cell matches -> far more hits than the first-pass capacity
+    a = "A" * 700
+    got = engine.dotdata(10, a, a)
+    exp = O.dotdata(10, a, a)
+    np.testing.assert_array_equal(got, exp)
+
+
+@pytest.mark.parametrize("seed,types", [(1, synth.SV_TYPES), (2, ("DEL",)), (3, ("TANDUP", "INV")), (4, ("INS",))])
+def test_workload_parity(engine, seed, types):
+    w = synth.make_workload(12, seed=seed, types=types, size_range=(50, 1500), reads_per_sv=8,
+                            max_miss=3, lowercase_every=5, k_choices=(10, 10, 20, 10, 30))
+    res = engine.score(w.batch)
+    exp = BO.score_batch(w.batch)
+    _compare(res, exp)
+    assert (res.task_status == 1).sum() > 0
+
+
+def test_modes_on_same_inputs(engine):
+    """Every mode on every SV type (the drivers use each mode on several SV classes)."""
+    rng = np.random.default_rng(9)
+    b = Batch()
+    for st in synth.SV_TYPES:
+        case = synth.make_sv_case(rng, st, int(rng.integers(200, 1200)), genotype=1)
+        ref_id, alt_id = b.add_seq(case.ref_seq), b.add_seq(case.alt_seq)
+        for mode in (MODE_ABS, MODE_W10, MODE_REDEF, MODE_ABS_AND_W10):
+            for hap in (case.hap_ref, case.hap_alt):
+                want = case.read_window
+                reads, _ = synth.simulate_reads(rng, hap, np.array([0]), np.array([min(len(hap), int(want * 1.12) + 60)]),
+                                                np.array([want]))
+                b.add_task(b.add_seq(reads), ref_id, alt_id, int(rng.integers(0, 4)), 10, mode)
+            b.end_sv(st)
+    pb = b.pack()
+    res = engine.score(pb)
+    _compare(res, BO.score_batch(pb))
+
+
+def test_empty_and_unscorable(engine):
+    b = Batch()
+    rng = np.random.default_rng(5)
+    ref = synth.random_dna(rng, 900); alt = synth.random_dna(rng, 700)
+    rid, aid = b.add_seq(ref), b.add_seq(alt)
+    b.add_task(b.add_seq(synth.random_dna(rng, 800)), rid, aid, 0, 10, MODE_ABS)      # unrelated read -> [0,0]
+    b.add_task(b.add_seq("ACGT"), rid, aid, 0, 10, MODE_W10)                          # read shorter than k
+    b.add_task(b.add_seq(""), rid, aid, 0, 10, MODE_REDEF)                            # empty read
+    b.end_sv("none")
+    b.end_sv("empty-sv")                                                              # SV without reads -> NA row
+    pb = b.pack()
+    res = engine.score(pb)
+    _compare(res, BO.score_batch(pb))
+    assert list(res.sv_gt) == [255, 255]
+
+
+def test_hit_budget_waves_identical(engine):
+    from vapor_b200.engine import Engine
+    w = synth.make_workload(10, seed=21, size_range=(50, 800), reads_per_sv=6)
+    base = engine.score(w.batch)
+    small = Engine(0, hit_budget_bytes=1 << 20)         # force many waves
+    try:
+        res = small.score(w.batch)
+        assert small.timings()["n_waves"] > 1
+    finally:
+        small.close()
+    for f in base.__dataclass_fields__:
+        np.testing.assert_array_equal(getattr(res, f), getattr(base, f))

@@ -1,0 +1,798 @@
+// vapor_b200 C-ABI: host-side planning + launches of kernels 1-4.  See include/vapor_b200.h.
+//
+// There is deliberately no CPU implementation of the scoring path in this file: every result
+// an entry point returns was computed by the kernels in k1..k4; without a CUDA device
+// vapor_gpu_open fails and nothing else can be called.
+#include "../../include/vapor_b200.h"
+#include "common.cuh"
+#include "k1_pack.cuh"
+#include "k2_tile.cuh"
+#include "k3_score.cuh"
+#include "k4_genotype.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace vb;
+
+namespace {
+
+std::string g_open_error;
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                  \
+            return VAPOR_E_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+template <typename T>
+struct DevBuf {                      // grow-only device buffer
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T>
+struct PinBuf {                      // grow-only pinned host staging buffer
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Wave {
+    int64_t task_begin, task_end;
+    int64_t plot_begin, plot_end;
+    int64_t hit_elems;
+};
+
+// kernel-3 scratch classes: bins that fit in shared memory, then a global-memory fallback
+constexpr int K3_NCLASS = 5;
+const int k3_class_cap[K3_NCLASS - 1] = {4096, 12288, 24576, 43000};
+
+struct Handle {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t hit_budget = 0;          // bytes; 0 = default
+
+    // plan (host)
+    std::vector<Operand> ops;
+    std::vector<Plot> plots;
+    std::vector<Task> tasks;
+    std::vector<int32_t> chunk_prefix;
+    std::vector<int64_t> strip_prefix;
+    std::vector<Wave> waves;
+    std::vector<int32_t> class_ids;              // task ids grouped by (wave, class)
+    std::vector<int64_t> class_off;              // [n_waves*K3_NCLASS+1]
+    int max_nb = 0;
+    int64_t n_task = 0, n_sv = 0, n_seq = 0, seq_total = 0;
+    int64_t hash_elems = 0, code_bytes = 0, max_wave_hits = 0;
+    bool resident = false, ran = false;
+    vapor_timings_t tm{};
+
+    // device
+    DevBuf<uint8_t> d_seq, d_code, d_task_status, d_sv_gt;
+    DevBuf<Operand> d_ops;
+    DevBuf<Plot> d_plots;
+    DevBuf<Task> d_tasks;
+    DevBuf<int32_t> d_chunk_prefix, d_op_status, d_class_ids, d_sv_nscore, d_ovf_ids;
+    DevBuf<int64_t> d_strip_prefix, d_sv_off, d_ovf_prefix;
+    DevBuf<uint32_t> d_hash, d_cnt, d_task_hits, d_gscratch, d_misc;
+    DevBuf<uint2> d_hits, d_ovf_hits;
+    DevBuf<double> d_task_score, d_task_stat, d_pos, d_sv_qs, d_sv_gs, d_sv_gq;
+    DevBuf<unsigned long long> d_task_hitsum, d_queue;
+    // pinned staging
+    PinBuf<uint8_t> p_seq;
+    PinBuf<uint32_t> p_misc;
+
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
+    struct Span { size_t ev; int cat; };
+    std::vector<Span> spans;
+};
+
+enum { CAT_H2D = 0, CAT_PACK, CAT_TILE, CAT_SCORE, CAT_GENO, CAT_D2H, CAT_N };
+
+int span_begin(Handle* h, int cat) {
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        h->ev_pool.push_back({a, b});
+    }
+    size_t i = h->ev_used++;
+    cudaEventRecord(h->ev_pool[i].first, h->stream);
+    h->spans.push_back({i, cat});
+    return (int)i;
+}
+void span_end(Handle* h, int i) { cudaEventRecord(h->ev_pool[i].second, h->stream); }
+
+void collect_spans(Handle* h, float* acc /*CAT_N*/) {
+    for (auto& s : h->spans) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev_pool[s.ev].first, h->ev_pool[s.ev].second);
+        acc[s.cat] += ms;
+    }
+    h->spans.clear();
+    h->ev_used = 0;
+}
+
+uint8_t host_code_lut[256];
+void build_lut() {
+    for (int i = 0; i < 256; ++i) host_code_lut[i] = CODE_INVALID;
+    const char* acgt = "ACGT";
+    for (int i = 0; i < 4; ++i) {
+        host_code_lut[(int)acgt[i]] = (uint8_t)i;
+        host_code_lut[(int)acgt[i] + 32] = (uint8_t)(8 + i);
+    }
+    host_code_lut[(int)'N'] = 4; host_code_lut[(int)'n'] = 12;
+    const char* iupac = "RYSWKMBDHV";                 // key_modify, Simple_function.pyx:909-948
+    for (int i = 0; i < 10; ++i) { host_code_lut[(int)iupac[i]] = 4; host_code_lut[(int)iupac[i] + 32] = 12; }
+}
+
+inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
+
+int k3_class_of(int nb) {
+    for (int c = 0; c < K3_NCLASS - 1; ++c) if (nb <= k3_class_cap[c]) return c;
+    return K3_NCLASS - 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// planning: operands (k-mer word arrays), plots, tasks, waves
+// ------------------------------------------------------------------------------------------
+int plan_batch(Handle* h, const vapor_batch_t* in) {
+    if (!in || !in->seq_off || (!in->seq_bytes && in->n_seq > 0)) { h->err = "NULL batch arrays"; return VAPOR_E_ARG; }
+    if (in->n_task > 0 && (!in->task_read || !in->task_ref || !in->task_alt || !in->task_miss || !in->task_k || !in->task_mode)) {
+        h->err = "NULL task arrays"; return VAPOR_E_ARG;
+    }
+    if (in->n_sv > 0 && !in->sv_task_off) { h->err = "NULL sv_task_off"; return VAPOR_E_ARG; }
+    const int64_t n_seq = in->n_seq, n_task = in->n_task, n_sv = in->n_sv;
+    for (int64_t i = 0; i < n_seq; ++i) {
+        int64_t L = in->seq_off[i + 1] - in->seq_off[i];
+        if (L < 0 || L >= (1ll << 27)) { h->err = "sequence length out of range (0 .. 2^27)"; return VAPOR_E_ARG; }
+    }
+    if (n_sv > 0 && (in->sv_task_off[0] != 0 || in->sv_task_off[n_sv] != n_task)) { h->err = "sv_task_off must cover [0, n_task]"; return VAPOR_E_ARG; }
+
+    h->ops.clear(); h->plots.clear(); h->tasks.clear(); h->waves.clear();
+    h->tasks.reserve(n_task);
+    h->plots.reserve(n_task * 2);
+    std::vector<int8_t> has_lower(n_seq, -1);
+    auto seq_has_lower = [&](int32_t s) -> bool {
+        if (has_lower[s] < 0) {
+            const uint8_t* p = in->seq_bytes + in->seq_off[s];
+            const int64_t L = in->seq_off[s + 1] - in->seq_off[s];
+            int8_t f = 0;
+            for (int64_t i = 0; i < L; ++i) if (p[i] >= 'a' && p[i] <= 'z') { f = 1; break; }
+            has_lower[s] = f;
+        }
+        return has_lower[s] != 0;
+    };
+
+    int64_t hash_off = 0, code_off = 0, cells = 0;
+    struct Key { int32_t seq, k, flags, op; };
+    std::vector<Key> local;                      // operand cache of the current SV
+    auto get_op = [&](int32_t seq, int k, int flags) -> int32_t {
+        for (auto& e : local) if (e.seq == seq && e.k == k && e.flags == flags) return e.op;
+        Operand o{};
+        o.seq_begin = in->seq_off[seq];
+        o.len = (int32_t)(in->seq_off[seq + 1] - in->seq_off[seq]);
+        o.k = k; o.flags = flags;
+        o.n = std::max(0, o.len - k + 1);
+        o.hash_off = hash_off; o.code_off = code_off;
+        hash_off += align4(o.n) + 8;
+        code_off += o.len + 8;
+        h->ops.push_back(o);
+        int32_t id = (int32_t)h->ops.size() - 1;
+        local.push_back({seq, k, flags, id});
+        return id;
+    };
+    auto add_plot = [&](int32_t rop, int32_t sop, int32_t miss) -> int32_t {
+        const Operand& r = h->ops[rop];
+        const Operand& s = h->ops[sop];
+        Plot p{};
+        p.read_op = rop; p.struct_op = sop; p.miss = miss;
+        p.n = r.n;
+        p.m = (miss <= s.len) ? std::max(0, s.len - miss - s.k + 1) : 0;
+        p.cap = (p.n > 0 && p.m > 0) ? (uint32_t)align4((int64_t)p.n + p.m + 32) : 0u;
+        p.hit_off = 0;
+        cells += (int64_t)p.n * p.m;
+        h->plots.push_back(p);
+        return (int32_t)h->plots.size() - 1;
+    };
+
+    int64_t sv_cursor = 0;
+    int64_t next_sv_end = n_sv > 0 ? in->sv_task_off[1] : n_task;
+    for (int64_t t = 0; t < n_task; ++t) {
+        while (n_sv > 0 && t >= next_sv_end && sv_cursor + 1 < n_sv) {
+            ++sv_cursor; next_sv_end = in->sv_task_off[sv_cursor + 1]; local.clear();
+        }
+        if (n_sv == 0 && (t & 63) == 0) local.clear();
+        const int32_t rs = in->task_read[t], fs = in->task_ref[t], as = in->task_alt[t];
+        const int32_t miss = in->task_miss[t];
+        const int k = in->task_k[t], mode = in->task_mode[t];
+        if (rs < 0 || rs >= n_seq || fs < 0 || fs >= n_seq || as < 0 || as >= n_seq) { h->err = "task sequence index out of range"; return VAPOR_E_ARG; }
+        if (k < 1 || k > K1_MAXK) { h->err = "window_size k must be 1..40"; return VAPOR_E_ARG; }
+        if (mode < 0 || mode > 3) { h->err = "unknown mode"; return VAPOR_E_ARG; }
+        if (miss < 0) { h->err = "miss_bp must be >= 0"; return VAPOR_E_ARG; }
+        Task tk{};
+        tk.mode = mode;
+        tk.len_ref = (int32_t)(in->seq_off[fs + 1] - in->seq_off[fs]);
+        tk.len_alt = (int32_t)(in->seq_off[as + 1] - in->seq_off[as]);
+        tk.read_op = get_op(rs, k, OPF_READ);
+        const bool abs_first = (mode == VAPOR_MODE_ABS || mode == VAPOR_MODE_ABS_AND_W10);
+        const int fl_ref = (abs_first && seq_has_lower(fs)) ? OPF_UPPER : 0;
+        const int fl_alt = (abs_first && seq_has_lower(as)) ? OPF_UPPER : 0;
+        tk.plot[0] = add_plot(tk.read_op, get_op(fs, k, fl_ref), miss);
+        tk.plot[1] = add_plot(tk.read_op, get_op(as, k, fl_alt), miss);
+        tk.plot[2] = tk.plot[3] = -1;
+        if (mode == VAPOR_MODE_ABS_AND_W10) {       // W10 does not upper-case (Simple_function.pyx:277-279)
+            tk.plot[2] = fl_ref ? add_plot(tk.read_op, get_op(fs, k, 0), miss) : tk.plot[0];
+            tk.plot[3] = fl_alt ? add_plot(tk.read_op, get_op(as, k, 0), miss) : tk.plot[1];
+        }
+        h->tasks.push_back(tk);
+    }
+
+    // k1 chunks
+    h->chunk_prefix.assign(h->ops.size() + 1, 0);
+    int64_t bases = 0;
+    for (size_t i = 0; i < h->ops.size(); ++i) {
+        int chunks = std::max(1, (h->ops[i].len + K1_CHUNK - 1) / K1_CHUNK);
+        h->chunk_prefix[i + 1] = h->chunk_prefix[i] + chunks;
+        bases += h->ops[i].len;
+    }
+    // strips + waves (plots were created in task order, so each wave is a contiguous plot range)
+    const int64_t budget_bytes = h->hit_budget > 0 ? h->hit_budget : (int64_t)6 << 30;
+    const int64_t budget_elems = std::max<int64_t>(budget_bytes / (int64_t)sizeof(uint2), 1 << 16);
+    h->strip_prefix.assign(h->plots.size() + 1, 0);
+    for (size_t i = 0; i < h->plots.size(); ++i) {
+        const Plot& p = h->plots[i];
+        int64_t strips = (p.n > 0 && p.m > 0)
+            ? (int64_t)((p.n + K2_ROWS - 1) / K2_ROWS) * (int64_t)((p.m + K2_TS - 1) / K2_TS) : 0;
+        h->strip_prefix[i + 1] = h->strip_prefix[i] + strips;
+    }
+    h->max_nb = 1; h->max_wave_hits = 0;
+    {
+        Wave w{0, 0, 0, 0, 0};
+        size_t pi = 0;
+        for (int64_t t = 0; t < n_task; ++t) {
+            int32_t last_plot = -1;
+            for (int i = 0; i < 4; ++i) last_plot = std::max(last_plot, h->tasks[t].plot[i]);
+            int64_t need = 0;
+            for (size_t q = pi; q <= (size_t)last_plot; ++q) need += h->plots[q].cap;
+            if (w.hit_elems + need > budget_elems && w.task_end > w.task_begin) {
+                h->waves.push_back(w);
+                w = Wave{t, t, (int64_t)pi, (int64_t)pi, 0};
+            }
+            for (size_t q = pi; q <= (size_t)last_plot; ++q) {
+                h->plots[q].hit_off = w.hit_elems;
+                w.hit_elems += h->plots[q].cap;
+                h->max_nb = std::max(h->max_nb, h->plots[q].n + h->plots[q].m - 1);
+            }
+            pi = (size_t)last_plot + 1;
+            w.task_end = t + 1; w.plot_end = (int64_t)pi;
+            h->max_wave_hits = std::max(h->max_wave_hits, w.hit_elems);
+        }
+        if (w.task_end > w.task_begin) h->waves.push_back(w);
+    }
+    // kernel-3 classes per wave
+    h->class_ids.resize(n_task);
+    h->class_off.assign(h->waves.size() * K3_NCLASS + 1, 0);
+    {
+        std::vector<int64_t> count(h->waves.size() * K3_NCLASS, 0);
+        std::vector<uint8_t> cls(n_task);
+        for (size_t wi = 0; wi < h->waves.size(); ++wi)
+            for (int64_t t = h->waves[wi].task_begin; t < h->waves[wi].task_end; ++t) {
+                int nb = 1;
+                for (int i = 0; i < 4; ++i) if (h->tasks[t].plot[i] >= 0) {
+                    const Plot& p = h->plots[h->tasks[t].plot[i]];
+                    nb = std::max(nb, p.n + p.m - 1);
+                }
+                cls[t] = (uint8_t)k3_class_of(nb);
+                ++count[wi * K3_NCLASS + cls[t]];
+            }
+        for (size_t i = 0; i < count.size(); ++i) h->class_off[i + 1] = h->class_off[i] + count[i];
+        std::vector<int64_t> cur(h->class_off.begin(), h->class_off.end() - 1);
+        for (size_t wi = 0; wi < h->waves.size(); ++wi)
+            for (int64_t t = h->waves[wi].task_begin; t < h->waves[wi].task_end; ++t)
+                h->class_ids[cur[wi * K3_NCLASS + cls[t]]++] = (int32_t)t;
+    }
+    h->n_task = n_task; h->n_sv = n_sv; h->n_seq = n_seq;
+    h->seq_total = n_seq > 0 ? in->seq_off[n_seq] : 0;
+    h->hash_elems = hash_off + 16; h->code_bytes = code_off + 64;
+    h->tm = vapor_timings_t{};
+    h->tm.cells = cells; h->tm.n_plots = (int64_t)h->plots.size(); h->tm.n_operands = (int64_t)h->ops.size();
+    h->tm.n_strips = h->strip_prefix.back(); h->tm.n_waves = (int64_t)h->waves.size(); h->tm.bases = bases;
+    return VAPOR_OK;
+}
+
+int upload_impl(Handle* h, const vapor_batch_t* in) {
+    h->resident = false; h->ran = false;
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = plan_batch(h, in);
+    if (rc) return rc;
+    h->tm.host_prep_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    CK(cudaSetDevice(h->device));
+    const size_t nt = (size_t)h->n_task, nsv = (size_t)h->n_sv;
+    CK(h->d_seq.ensure((size_t)h->seq_total + 64));
+    CK(h->d_ops.ensure(h->ops.size() + 1));
+    CK(h->d_plots.ensure(h->plots.size() + 1));
+    CK(h->d_tasks.ensure(nt + 1));
+    CK(h->d_chunk_prefix.ensure(h->chunk_prefix.size()));
+    CK(h->d_strip_prefix.ensure(h->strip_prefix.size()));
+    CK(h->d_class_ids.ensure(nt + 1));
+    CK(h->d_sv_off.ensure(nsv + 1));
+    CK(h->d_hash.ensure((size_t)h->hash_elems));
+    CK(h->d_code.ensure((size_t)h->code_bytes));
+    CK(h->d_op_status.ensure(h->ops.size() + 1));
+    CK(h->d_cnt.ensure(h->plots.size() + 1));
+    CK(h->d_hits.ensure((size_t)h->max_wave_hits + 64));
+    CK(h->d_task_score.ensure(nt + 1)); CK(h->d_task_status.ensure(nt + 1));
+    CK(h->d_task_stat.ensure(4 * nt + 4)); CK(h->d_task_hits.ensure(4 * nt + 4)); CK(h->d_task_hitsum.ensure(4 * nt + 4));
+    CK(h->d_pos.ensure(nt + 1));
+    CK(h->d_sv_qs.ensure(nsv + 1)); CK(h->d_sv_gs.ensure(nsv + 1)); CK(h->d_sv_gq.ensure(nsv + 1));
+    CK(h->d_sv_gt.ensure(nsv + 1)); CK(h->d_sv_nscore.ensure(nsv + 1));
+    CK(h->d_queue.ensure(4)); CK(h->d_misc.ensure(16));
+    if (k3_class_of(h->max_nb) == K3_NCLASS - 1)
+        CK(h->d_gscratch.ensure((size_t)2 * h->sm_count * k3_scratch_words(h->max_nb)));
+
+    int sp = span_begin(h, CAT_H2D);
+    if (h->seq_total > 0) CK(cudaMemcpyAsync(h->d_seq.p, in->seq_bytes, (size_t)h->seq_total, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_ops.p, h->ops.data(), h->ops.size() * sizeof(Operand), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_plots.p, h->plots.data(), h->plots.size() * sizeof(Plot), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_tasks.p, h->tasks.data(), nt * sizeof(Task), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_chunk_prefix.p, h->chunk_prefix.data(), h->chunk_prefix.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_strip_prefix.p, h->strip_prefix.data(), h->strip_prefix.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_class_ids.p, h->class_ids.data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (nsv) CK(cudaMemcpyAsync(h->d_sv_off.p, in->sv_task_off, (nsv + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    span_end(h, sp);
+    CK(cudaStreamSynchronize(h->stream));
+    float acc[CAT_N] = {0};
+    collect_spans(h, acc);
+    h->tm.h2d_ms = acc[CAT_H2D];
+    h->resident = true;
+    return VAPOR_OK;
+}
+
+}  // namespace
+
+namespace {
+
+int run_impl(Handle* h) {
+    if (!h->resident) { h->err = "no resident batch: call vapor_gpu_upload first"; return VAPOR_E_STATE; }
+    CK(cudaSetDevice(h->device));
+    const size_t nt = (size_t)h->n_task, nsv = (size_t)h->n_sv;
+    int64_t launches = 0;
+    h->tm.n_overflow_plots = 0;
+    cudaEvent_t ev_total0, ev_total1;
+    CK(cudaEventCreate(&ev_total0)); CK(cudaEventCreate(&ev_total1));
+    CK(cudaEventRecord(ev_total0, h->stream));
+
+    // ---- kernel 1 -------------------------------------------------------------------------
+    int sp = span_begin(h, CAT_PACK);
+    CK(cudaMemsetAsync(h->d_op_status.p, 0, (h->ops.size() + 1) * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(h->d_cnt.p, 0, (h->plots.size() + 1) * sizeof(uint32_t), h->stream));
+    if (!h->ops.empty()) {
+        k1_pack_kmers<<<h->chunk_prefix.back(), K1_THREADS, 0, h->stream>>>(
+            h->d_seq.p, h->d_ops.p, h->d_chunk_prefix.p, (int)h->ops.size(), h->d_hash.p, h->d_code.p, h->d_op_status.p);
+        ++launches;
+    }
+    span_end(h, sp);
+    CK(cudaGetLastError());
+
+    std::vector<uint32_t> cnt_host;
+    for (size_t wi = 0; wi < h->waves.size(); ++wi) {
+        const Wave& w = h->waves[wi];
+        const int n_plots = (int)(w.plot_end - w.plot_begin);
+        const int64_t sbase = h->strip_prefix[w.plot_begin];
+        const int64_t n_strips = h->strip_prefix[w.plot_end] - sbase;
+        // ---- kernel 2 ---------------------------------------------------------------------
+        sp = span_begin(h, CAT_TILE);
+        CK(cudaMemsetAsync(h->d_queue.p, 0, 4 * sizeof(unsigned long long), h->stream));
+        CK(cudaMemsetAsync(h->d_misc.p, 0, 16 * sizeof(uint32_t), h->stream));
+        if (n_strips > 0) {
+            K2Params kp{};
+            kp.plots = h->d_plots.p + w.plot_begin;
+            kp.ops = h->d_ops.p;
+            kp.strip_prefix = h->d_strip_prefix.p + w.plot_begin;
+            kp.n_plots = n_plots;
+            kp.n_strips = n_strips;
+            kp.strip_base = sbase;
+            kp.hash = h->d_hash.p; kp.code = h->d_code.p;
+            kp.hits = h->d_hits.p;
+            kp.cnt = h->d_cnt.p + w.plot_begin;
+            kp.queue = h->d_queue.p;
+            kp.overflow = h->d_misc.p;
+            const int64_t warps_needed = n_strips;
+            int grid = (int)std::min<int64_t>((warps_needed + K2_WARPS - 1) / K2_WARPS, (int64_t)h->sm_count * 8);
+            k2_tile_match<<<grid, K2_THREADS, 0, h->stream>>>(kp);
+            ++launches;
+        }
+        span_end(h, sp);
+        CK(cudaGetLastError());
+        // ---- overflow check: plots that found more hits than their first-pass capacity --------
+        uint32_t ovf = 0;
+        CK(cudaMemcpyAsync(&ovf, h->d_misc.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (ovf) {
+            cnt_host.resize(n_plots);
+            CK(cudaMemcpy(cnt_host.data(), h->d_cnt.p + w.plot_begin, n_plots * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            std::vector<Plot> re_plots; std::vector<int64_t> re_prefix{0}; std::vector<int32_t> re_ids;
+            int64_t extra = 0;
+            for (int i = 0; i < n_plots; ++i) {
+                Plot& p = h->plots[w.plot_begin + i];
+                if (cnt_host[i] > p.cap) {
+                    if (cnt_host[i] > (1u << 30)) { h->err = "a plot produced more than 2^30 hits"; return VAPOR_E_CAPACITY; }
+                    p.cap = (uint32_t)align4(cnt_host[i]);
+                    p.hit_off = extra;                       // relative to the overflow buffer
+                    extra += p.cap;
+                    re_plots.push_back(p); re_ids.push_back(i);
+                    re_prefix.push_back(re_prefix.back() + (h->strip_prefix[w.plot_begin + i + 1] - h->strip_prefix[w.plot_begin + i]));
+                }
+            }
+            h->tm.n_overflow_plots += (int64_t)re_plots.size();
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            if ((size_t)extra * sizeof(uint2) + ((size_t)1 << 30) > free_b + h->d_ovf_hits.cap * sizeof(uint2)) {
+                h->err = "hit lists of repetitive plots exceed device memory"; return VAPOR_E_CAPACITY;
+            }
+            CK(h->d_ovf_hits.ensure((size_t)extra + 64));
+            // express overflow hit offsets relative to d_hits so kernel 3 needs one base pointer
+            const int64_t delta = (int64_t)(h->d_ovf_hits.p - h->d_hits.p);
+            DevBuf<Plot> d_re; DevBuf<uint32_t> d_recnt;
+            CK(d_re.ensure(re_plots.size())); CK(d_recnt.ensure(re_plots.size()));
+            CK(h->d_ovf_prefix.ensure(re_prefix.size()));
+            for (size_t i = 0; i < re_plots.size(); ++i) {
+                re_plots[i].hit_off += delta;
+                h->plots[w.plot_begin + re_ids[i]].hit_off = re_plots[i].hit_off;
+            }
+            CK(cudaMemcpy(d_re.p, re_plots.data(), re_plots.size() * sizeof(Plot), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(h->d_ovf_prefix.p, re_prefix.data(), re_prefix.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(h->d_plots.p + w.plot_begin, &h->plots[w.plot_begin], n_plots * sizeof(Plot), cudaMemcpyHostToDevice));
+            CK(cudaMemset(d_recnt.p, 0, re_plots.size() * sizeof(uint32_t)));
+            CK(cudaMemsetAsync(h->d_queue.p, 0, 4 * sizeof(unsigned long long), h->stream));
+            CK(cudaMemsetAsync(h->d_misc.p, 0, 16 * sizeof(uint32_t), h->stream));
+            sp = span_begin(h, CAT_TILE);
+            K2Params kp{};
+            kp.plots = d_re.p; kp.ops = h->d_ops.p; kp.strip_prefix = h->d_ovf_prefix.p;
+            kp.n_plots = (int)re_plots.size(); kp.n_strips = re_prefix.back(); kp.strip_base = 0;
+            kp.hash = h->d_hash.p; kp.code = h->d_code.p; kp.hits = h->d_hits.p;
+            kp.cnt = d_recnt.p; kp.queue = h->d_queue.p; kp.overflow = h->d_misc.p;
+            int grid = (int)std::min<int64_t>((kp.n_strips + K2_WARPS - 1) / K2_WARPS, (int64_t)h->sm_count * 8);
+            k2_tile_match<<<grid, K2_THREADS, 0, h->stream>>>(kp);
+            ++launches;
+            span_end(h, sp);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(h->stream));
+            d_re.release(); d_recnt.release();
+        }
+        // ---- kernel 3, one launch per scratch class ----------------------------------------------
+        sp = span_begin(h, CAT_SCORE);
+        for (int c = 0; c < K3_NCLASS; ++c) {
+            const int64_t o0 = h->class_off[wi * K3_NCLASS + c], o1 = h->class_off[wi * K3_NCLASS + c + 1];
+            if (o1 == o0) continue;
+            K3Params kp{};
+            kp.tasks = h->d_tasks.p; kp.task_ids = h->d_class_ids.p + o0; kp.n_ids = (int)(o1 - o0);
+            kp.plots = h->d_plots.p; kp.cnt = h->d_cnt.p; kp.op_status = h->d_op_status.p;
+            kp.hits = h->d_hits.p;
+            kp.task_score = h->d_task_score.p; kp.task_status = h->d_task_status.p; kp.task_stat = h->d_task_stat.p;
+            kp.task_hits = h->d_task_hits.p; kp.task_hitsum = h->d_task_hitsum.p;
+            if (c < K3_NCLASS - 1) {
+                kp.nb_cap = k3_class_cap[c]; kp.use_global = 0; kp.gscratch = nullptr;
+                const size_t smem = k3_scratch_words(kp.nb_cap) * sizeof(uint32_t);
+                k3_score_reads<<<kp.n_ids, K3_THREADS, smem, h->stream>>>(kp);
+            } else {
+                kp.nb_cap = h->max_nb; kp.use_global = 1; kp.gscratch = h->d_gscratch.p;
+                const int grid = std::min(kp.n_ids, 2 * h->sm_count);
+                k3_score_reads<<<grid, K3_THREADS, 0, h->stream>>>(kp);
+            }
+            ++launches;
+        }
+        span_end(h, sp);
+        CK(cudaGetLastError());
+    }
+    // ---- kernel 4 -------------------------------------------------------------------------
+    sp = span_begin(h, CAT_GENO);
+    if (nsv) {
+        k4_genotype<<<(unsigned)((nsv + 127) / 128), 128, 0, h->stream>>>(
+            h->d_sv_off.p, (int)nsv, h->d_task_score.p, h->d_task_status.p, h->d_pos.p,
+            h->d_sv_qs.p, h->d_sv_gs.p, h->d_sv_gq.p, h->d_sv_gt.p, h->d_sv_nscore.p);
+        ++launches;
+    }
+    span_end(h, sp);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev_total1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float acc[CAT_N] = {0};
+    collect_spans(h, acc);
+    h->tm.pack_ms = acc[CAT_PACK]; h->tm.tile_ms = acc[CAT_TILE]; h->tm.score_ms = acc[CAT_SCORE]; h->tm.genotype_ms = acc[CAT_GENO];
+    float tot = 0; cudaEventElapsedTime(&tot, ev_total0, ev_total1);
+    h->tm.total_ms = tot;
+    cudaEventDestroy(ev_total0); cudaEventDestroy(ev_total1);
+    h->tm.launches = launches;
+    // total hits
+    {
+        std::vector<uint32_t> c(h->plots.size());
+        if (!c.empty()) CK(cudaMemcpy(c.data(), h->d_cnt.p, c.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        int64_t tot_hits = 0;
+        for (auto v : c) tot_hits += v;
+        h->tm.hits = tot_hits;
+    }
+    (void)nt;
+    h->ran = true;
+    return VAPOR_OK;
+}
+
+int fetch_impl(Handle* h, vapor_out_t* out) {
+    if (!h->ran) { h->err = "nothing to fetch: call vapor_gpu_run first"; return VAPOR_E_STATE; }
+    if (!out) { h->err = "NULL out"; return VAPOR_E_ARG; }
+    CK(cudaSetDevice(h->device));
+    const size_t nt = (size_t)h->n_task, nsv = (size_t)h->n_sv;
+    int sp = span_begin(h, CAT_D2H);
+    if (nt) {
+        if (out->task_score) CK(cudaMemcpyAsync(out->task_score, h->d_task_score.p, nt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (out->task_status) CK(cudaMemcpyAsync(out->task_status, h->d_task_status.p, nt, cudaMemcpyDeviceToHost, h->stream));
+        if (out->task_stat) CK(cudaMemcpyAsync(out->task_stat, h->d_task_stat.p, 4 * nt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (out->task_hits) CK(cudaMemcpyAsync(out->task_hits, h->d_task_hits.p, 4 * nt * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        if (out->task_hitsum) CK(cudaMemcpyAsync(out->task_hitsum, h->d_task_hitsum.p, 4 * nt * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (nsv) {
+        if (out->sv_qs) CK(cudaMemcpyAsync(out->sv_qs, h->d_sv_qs.p, nsv * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (out->sv_gs) CK(cudaMemcpyAsync(out->sv_gs, h->d_sv_gs.p, nsv * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (out->sv_gq) CK(cudaMemcpyAsync(out->sv_gq, h->d_sv_gq.p, nsv * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (out->sv_gt) CK(cudaMemcpyAsync(out->sv_gt, h->d_sv_gt.p, nsv, cudaMemcpyDeviceToHost, h->stream));
+        if (out->sv_nscore) CK(cudaMemcpyAsync(out->sv_nscore, h->d_sv_nscore.p, nsv * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    span_end(h, sp);
+    CK(cudaStreamSynchronize(h->stream));
+    float acc[CAT_N] = {0};
+    collect_spans(h, acc);
+    h->tm.d2h_ms = acc[CAT_D2H];
+    return VAPOR_OK;
+}
+
+// ---- integer issue-rate microbenchmarks ------------------------------------------------------
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_int_peak(const uint32_t* __restrict__ in, uint32_t* out, int iters) {
+    uint32_t r[32];
+    #pragma unroll
+    for (int q = 0; q < 32; ++q) r[q] = in[(threadIdx.x + q * 7) & 1023];
+    uint32_t v = in[threadIdx.x & 1023];
+    if (WHICH == 0) {
+        bool p0 = false, p1 = false, p2 = false, p3 = false;
+        for (int it = 0; it < iters; ++it) {
+            #pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+                p0 |= (r[q] == v); p1 |= (r[q + 1] == v); p2 |= (r[q + 2] == v); p3 |= (r[q + 3] == v);
+            }
+            v += 0x9E3779B9u;
+        }
+        if (p0 | p1 | p2 | p3) out[0] = v;
+    } else if (WHICH == 1) {
+        for (int it = 0; it < iters; ++it) {
+            #pragma unroll
+            for (int q = 0; q < 32; ++q) r[q] = (r[q] ^ v) & (r[(q + 1) & 31] | v);
+            v += 0x9E3779B9u;
+        }
+        uint32_t a = 0;
+        #pragma unroll
+        for (int q = 0; q < 32; ++q) a ^= r[q];
+        if (a == 0x12345678u) out[0] = a;
+    } else {
+        for (int it = 0; it < iters; ++it) {
+            #pragma unroll
+            for (int q = 0; q < 32; ++q) r[q] = r[q] + v + r[(q + 5) & 31];
+            v += 0x9E3779B9u;
+        }
+        uint32_t a = 0;
+        #pragma unroll
+        for (int q = 0; q < 32; ++q) a ^= r[q];
+        if (a == 0x12345678u) out[0] = a;
+    }
+}
+
+}  // namespace
+
+// ==============================================================================================
+// extern "C"
+// ==============================================================================================
+extern "C" {
+
+int vapor_b200_abi_version(void) { return VAPOR_B200_ABI_VERSION; }
+
+uint64_t vapor_hit_mix(uint32_t x, uint32_t y) { return hit_mix(x, y); }
+
+const char* vapor_gpu_last_error(void* handle) {
+    if (!handle) return g_open_error.c_str();
+    return static_cast<Handle*>(handle)->err.c_str();
+}
+
+int vapor_gpu_open(int device, void** handle) {
+    if (!handle) { g_open_error = "NULL handle pointer"; return VAPOR_E_ARG; }
+    *handle = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_open_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); vapor_b200 has no CPU fallback";
+        return VAPOR_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_open_error = "device index out of range"; return VAPOR_E_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_open_error = cudaGetErrorString(e); return VAPOR_E_CUDA; }
+    Handle* h = new Handle();
+    h->device = device;
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, device);
+    h->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { g_open_error = cudaGetErrorString(e); delete h; return VAPOR_E_CUDA; }
+    build_lut();
+    e = cudaMemcpyToSymbol(c_code_lut, host_code_lut, 256);
+    if (e != cudaSuccess) { g_open_error = std::string("kernel image not loadable on this device: ") + cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return VAPOR_E_CUDA; }
+    e = cudaFuncSetAttribute(k3_score_reads, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(k3_scratch_words(k3_class_cap[K3_NCLASS - 2]) * sizeof(uint32_t)));
+    if (e != cudaSuccess) { g_open_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return VAPOR_E_CUDA; }
+    *handle = h;
+    return VAPOR_OK;
+}
+
+int vapor_gpu_close(void* handle) {
+    if (!handle) return VAPOR_E_ARG;
+    Handle* h = static_cast<Handle*>(handle);
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->d_seq.release(); h->d_code.release(); h->d_task_status.release(); h->d_sv_gt.release();
+    h->d_ops.release(); h->d_plots.release(); h->d_tasks.release();
+    h->d_chunk_prefix.release(); h->d_op_status.release(); h->d_class_ids.release(); h->d_sv_nscore.release(); h->d_ovf_ids.release();
+    h->d_strip_prefix.release(); h->d_sv_off.release(); h->d_ovf_prefix.release();
+    h->d_hash.release(); h->d_cnt.release(); h->d_task_hits.release(); h->d_gscratch.release(); h->d_misc.release();
+    h->d_hits.release(); h->d_ovf_hits.release();
+    h->d_task_score.release(); h->d_task_stat.release(); h->d_pos.release(); h->d_sv_qs.release(); h->d_sv_gs.release(); h->d_sv_gq.release();
+    h->d_task_hitsum.release(); h->d_queue.release();
+    h->p_seq.release(); h->p_misc.release();
+    for (auto& ev : h->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return VAPOR_OK;
+}
+
+int vapor_gpu_set_hit_budget(void* handle, int64_t bytes) {
+    if (!handle) return VAPOR_E_ARG;
+    static_cast<Handle*>(handle)->hit_budget = bytes;
+    return VAPOR_OK;
+}
+
+int vapor_gpu_upload(void* handle, const vapor_batch_t* in) {
+    if (!handle) return VAPOR_E_ARG;
+    return upload_impl(static_cast<Handle*>(handle), in);
+}
+int vapor_gpu_run(void* handle) {
+    if (!handle) return VAPOR_E_ARG;
+    return run_impl(static_cast<Handle*>(handle));
+}
+int vapor_gpu_fetch(void* handle, vapor_out_t* out) {
+    if (!handle) return VAPOR_E_ARG;
+    return fetch_impl(static_cast<Handle*>(handle), out);
+}
+int vapor_gpu_score(void* handle, const vapor_batch_t* in, vapor_out_t* out) {
+    if (!handle) return VAPOR_E_ARG;
+    Handle* h = static_cast<Handle*>(handle);
+    int rc = upload_impl(h, in);
+    if (rc) return rc;
+    rc = run_impl(h);
+    if (rc) return rc;
+    return fetch_impl(h, out);
+}
+
+int vapor_gpu_last_timings(void* handle, vapor_timings_t* t) {
+    if (!handle || !t) return VAPOR_E_ARG;
+    *t = static_cast<Handle*>(handle)->tm;
+    return VAPOR_OK;
+}
+
+int vapor_gpu_dotdata(void* handle, int k, const uint8_t* read, int64_t read_len,
+                      const uint8_t* structure, int64_t struct_len,
+                      int32_t* xy, int64_t cap, int64_t* n_hits)
+{
+    if (!handle) return VAPOR_E_ARG;
+    Handle* h = static_cast<Handle*>(handle);
+    if (!n_hits || read_len < 0 || struct_len < 0 || (cap > 0 && !xy)) { h->err = "bad dotdata arguments"; return VAPOR_E_ARG; }
+    // one task in W10 mode (no upper-casing) over (read, structure, structure): plot 0 is the wanted plot
+    std::vector<uint8_t> seq((size_t)(read_len + struct_len));
+    if (read_len) memcpy(seq.data(), read, (size_t)read_len);
+    if (struct_len) memcpy(seq.data() + read_len, structure, (size_t)struct_len);
+    int64_t off[3] = {0, read_len, read_len + struct_len};
+    int32_t tr = 0, tf = 1, ta = 1, tmiss = 0;
+    uint8_t tk = (uint8_t)k, tm_ = VAPOR_MODE_W10;
+    int64_t sv_off[2] = {0, 1};
+    vapor_batch_t b{};
+    b.seq_bytes = seq.data(); b.seq_off = off; b.n_seq = 2; b.n_task = 1;
+    b.task_read = &tr; b.task_ref = &tf; b.task_alt = &ta; b.task_miss = &tmiss; b.task_k = &tk; b.task_mode = &tm_;
+    b.n_sv = 1; b.sv_task_off = sv_off;
+    if (k < 1 || k > K1_MAXK) { h->err = "window_size k must be 1..40"; return VAPOR_E_ARG; }
+    int rc = upload_impl(h, &b);
+    if (rc) return rc;
+    rc = run_impl(h);
+    if (rc) return rc;
+    int32_t st = 0;
+    CK(cudaMemcpy(&st, h->d_op_status.p + h->tasks[0].read_op, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (st) { h->err = "BADREAD: read holds a character outside ACGTN/acgtn after key_modify (reference raises KeyError)"; return VAPOR_E_ARG; }
+    const Plot& p = h->plots[h->tasks[0].plot[0]];
+    uint32_t cnt = 0;
+    CK(cudaMemcpy(&cnt, h->d_cnt.p + h->tasks[0].plot[0], sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    *n_hits = cnt;
+    std::vector<uint2> hits(cnt);
+    if (cnt) CK(cudaMemcpy(hits.data(), h->d_hits.p + p.hit_off, cnt * sizeof(uint2), cudaMemcpyDeviceToHost));
+    for (auto& v : hits) v.y &= HIT_Y_MASK;
+    std::sort(hits.begin(), hits.end(), [](const uint2& a, const uint2& b2) { return a.x != b2.x ? a.x < b2.x : a.y < b2.y; });
+    const int64_t nw = std::min<int64_t>(cap, cnt);
+    for (int64_t i = 0; i < nw; ++i) { xy[2 * i] = (int32_t)hits[i].x; xy[2 * i + 1] = (int32_t)hits[i].y; }
+    return VAPOR_OK;
+}
+
+int vapor_gpu_host_alloc(void** p, int64_t bytes) {
+    if (!p || bytes < 0) return VAPOR_E_ARG;
+    cudaError_t e = cudaMallocHost(p, (size_t)std::max<int64_t>(bytes, 1));
+    if (e != cudaSuccess) { g_open_error = cudaGetErrorString(e); return VAPOR_E_CUDA; }
+    return VAPOR_OK;
+}
+int vapor_gpu_host_free(void* p) {
+    if (!p) return VAPOR_OK;
+    return cudaFreeHost(p) == cudaSuccess ? VAPOR_OK : VAPOR_E_CUDA;
+}
+
+int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s) {
+    if (!handle || !lane_ops_per_s || which < 0 || which > 2) return VAPOR_E_ARG;
+    Handle* h = static_cast<Handle*>(handle);
+    CK(cudaSetDevice(h->device));
+    DevBuf<uint32_t> in, out;
+    CK(in.ensure(1024)); CK(out.ensure(4));
+    std::vector<uint32_t> hin(1024);
+    for (int i = 0; i < 1024; ++i) hin[i] = 0x01000193u * (uint32_t)(i + 1) ^ 0xA5A5A5A5u;
+    CK(cudaMemcpy(in.p, hin.data(), 1024 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    const int grid = h->sm_count * 8, iters = 1 << 15;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(a, h->stream));
+        if (which == 0) k_int_peak<0><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
+        else if (which == 1) k_int_peak<1><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
+        else k_int_peak<2><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
+        CK(cudaEventRecord(b, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        const double ops = (double)grid * 256.0 * (double)iters * 32.0;
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    in.release(); out.release();
+    *lane_ops_per_s = best;
+    return VAPOR_OK;
+}
+
+}  // extern "C"

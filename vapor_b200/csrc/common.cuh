@@ -1,0 +1,65 @@
+// Shared definitions for the vapor_b200 kernels (sm_100a).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vb {
+
+// ---- alphabet after key_modify (reference: vapor_vali/Simple_function.pyx:908-949) ----
+// codes: A0 C1 G2 T3 N4  a8 c9 g10 t11 n12, IUPAC RYSWKMBDHV -> N(4) / n(12), anything else 15.
+constexpr int CODE_INVALID = 15;
+
+// ---- k-mer hash sentinels --------------------------------------------------------------
+constexpr uint32_t H_STRUCT_INVALID = 0xFFFFFFFFu;  // structure k-mer that can never match (holds 'X', ...)
+constexpr uint32_t H_READ_PAD       = 0xFFFFFFFEu;  // read padding / rejected read k-mer
+constexpr uint32_t H_MAX_VALID      = 0xFFFFFFFDu;
+constexpr uint32_t H_NEEDS_VERIFY   = 0x80000000u;  // bit 31: hash is not injective, confirm on the code strings
+
+// operand flags
+constexpr int OPF_UPPER = 1;   // str.upper() applied (ABS mode upper-cases ref/alt, Simple_function.pyx:183-184)
+constexpr int OPF_READ  = 2;   // read side: reverse complement also matches; invalid characters are an error
+
+struct Operand {           // one (sequence, k, casing, role): owns a k-mer hash array and a code array
+    int64_t seq_begin;     // byte offset in seq_bytes
+    int64_t hash_off;      // element offset in d_hash (multiple of 4)
+    int64_t code_off;      // byte offset in d_code
+    int32_t len;           // bases
+    int32_t n;             // k-mers = max(0, len-k+1)
+    int32_t k;
+    int32_t flags;
+};
+
+struct Plot {              // one recurrence plot: read operand x structure operand cut at miss
+    int64_t hit_off;       // element offset (uint2) of this plot's hit list
+    int32_t read_op, struct_op;
+    int32_t miss;          // structure is cut [miss:]
+    int32_t n, m;          // read k-mers, structure k-mers after the cut
+    uint32_t cap;          // capacity of the hit list
+};
+
+struct Task {              // one read of one SV/allele
+    int32_t plot[4];       // ref, alt of evaluation A; ref, alt of the W10 evaluation of ABS_AND_W10 (else -1)
+    int32_t len_ref, len_alt;   // full structure lengths: gate denominators (Simple_function.pyx:188-189)
+    int32_t read_op;
+    int32_t mode;
+};
+
+// hits carry two flag bits in y while kernel 3 works on them
+constexpr uint32_t HIT_Y_MASK   = 0x0FFFFFFFu;
+constexpr uint32_t HIT_F_KEEP1  = 0x40000000u;  // kept by the first (diagonal) clustering
+constexpr uint32_t HIT_F_CLEAN  = 0x80000000u;  // member of the cleaned dot set
+
+__host__ __device__ __forceinline__ uint64_t hit_mix(uint32_t x, uint32_t y) {
+    uint64_t z = ((uint64_t)x << 32) | (uint64_t)y;
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ int comp_code(int c) {
+    // invert_base in code space (Simple_function.pyx:20): A<->T, C<->G, N->N, case preserved
+    return (c & 4) ? c : (c ^ 3);
+}
+
+}  // namespace vb

@@ -1,0 +1,561 @@
+// Kernel 3: dot cleaning + diagonal-distance statistics + gates + per-read score.
+//
+// One CTA per task (= one read of one SV/allele).  It restates, on the sparse hit lists of
+// kernel 2, the reference functions
+//   dis_cluster_2 / clean_dotdata_diagnal_and_anti_diagnal   vapor_vali/Simple_function.pyx:566-580, 432-448
+//   dis_cluster / clean_dotdata_(anti_)diagnal_m1b            :551-564, 404-430
+//   eu_dis_abs_calcu, eu_dis_dots_within_10perc               :705-708, 730-733
+//   dis_to_diagnal_most_abundant_defined (+number_cluster,
+//     find_longest_list, unify_list), eu_dis_dir_calcu         :582-591, 1104-1118, 788-792, 710-722
+//   the three calcu_vapor_single_read_score_* gate ladders     :182-203, 241-257, 277-294
+//   and the per-read combine of the L2 drivers                 :1718-1726, 1913-1915
+//
+// The reference clusters by sorting; here a value histogram over y-x (resp. y+x) in shared
+// memory plays the sorted list: chain groups ("successive difference < 10") are runs of
+// occupied bins separated by >= 9 empty bins, found with bitmaps + popc, their sizes with one
+// block-wide prefix sum.  All statistics are exact integer sums; the only floating-point
+// operations are the final IEEE divisions the reference also performs, so results are
+// bit-identical, not merely within tolerance.
+#pragma once
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int K3_THREADS = 256;
+
+// scratch layout in 32-bit words for a capacity of NB bins
+__host__ __device__ inline int k3_words_bitmap(int nb) { return (nb + 31) / 32 + 1; }
+__host__ __device__ inline int k3_words_groups(int nb) { return nb / 10 + 4; }
+__host__ __device__ inline size_t k3_scratch_words(int nb) {
+    return (size_t)nb + 3 * (size_t)k3_words_bitmap(nb) + 2 * (size_t)k3_words_groups(nb) + 8;
+}
+
+struct K3Scratch {
+    uint32_t* P;        // [nb]   histogram, then inclusive prefix sum
+    uint32_t* present;  // bitmap of occupied bins
+    uint32_t* start;    // bitmap of group starts
+    uint32_t* wpref;    // [W+1] exclusive prefix of popc(start[w])
+    uint32_t* slist;    // [ng+1] start bin of every group (+ sentinel nb)
+    uint32_t* gsize;    // [ng]   hits in every group
+};
+
+struct K3Shared {       // block-wide accumulators (static shared memory)
+    unsigned long long u64a, u64b;
+    long long s64;
+    unsigned int u32a, u32b, u32c, gmax;
+    int imin, imax;
+    int ng;
+    unsigned int cnt11[11];
+    int sel;            // selected bin or -1
+    int m2min, m2max;
+    long long icpt2;    // twice the intercept
+    unsigned int warp_tot[K3_THREADS / 32];
+};
+
+__device__ __forceinline__ void k3_setup_scratch(K3Scratch& s, uint32_t* base, int nb_cap) {
+    const int wb = k3_words_bitmap(nb_cap), wg = k3_words_groups(nb_cap);
+    s.P = base;
+    s.present = s.P + nb_cap;
+    s.start = s.present + wb;
+    s.wpref = s.start + wb;
+    s.slist = s.wpref + wb;
+    s.gsize = s.slist + wg;
+}
+
+// inclusive prefix sum of arr[0..N) in place; every thread of the block must call it
+__device__ void k3_block_scan(uint32_t* arr, int N, K3Shared& sh) {
+    const int tid = threadIdx.x, T = K3_THREADS;
+    int C = (N + T - 1) / T;
+    C |= 1;                                            // odd chunk: conflict-free strided access
+    const int b0 = min(tid * C, N), b1 = min(b0 + C, N);
+    uint32_t sum = 0;
+    for (int i = b0; i < b1; ++i) sum += arr[i];
+    uint32_t inc = sum;
+    const int lane = tid & 31, warp = tid >> 5;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) sh.warp_tot[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; ++w) base += sh.warp_tot[w];
+    uint32_t run = base + inc - sum;
+    for (int i = b0; i < b1; ++i) { run += arr[i]; arr[i] = run; }
+    __syncthreads();
+}
+
+// From the histogram in s.P[0..nb) build the chain groups (runs of occupied bins whose gaps are
+// < 10) and their sizes.  On return s.P holds the inclusive prefix sum, sh.ng the group count,
+// sh.gmax the largest group.  Every thread of the block must call it.
+__device__ void k3_build_groups(K3Scratch& s, int nb, K3Shared& sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = (nb + 31) >> 5;
+    for (int w = warp; w < W; w += K3_THREADS / 32) {
+        const int b = w * 32 + lane;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, b < nb && s.P[b] != 0);
+        if (lane == 0) s.present[w] = bal;
+    }
+    if (tid == 0) { sh.gmax = 0; s.wpref[0] = 0; }
+    __syncthreads();
+    for (int w = tid; w < W; w += K3_THREADS) {
+        const uint32_t cur = s.present[w], prev = w ? s.present[w - 1] : 0u;
+        const unsigned long long comb = ((unsigned long long)cur << 32) | prev;
+        unsigned long long near = 0;
+        #pragma unroll
+        for (int sft = 1; sft <= 9; ++sft) near |= comb << sft;
+        const uint32_t st = cur & ~(uint32_t)(near >> 32);
+        s.start[w] = st;
+        s.wpref[w + 1] = __popc(st);
+    }
+    __syncthreads();
+    k3_block_scan(s.P, nb, sh);
+    k3_block_scan(s.wpref + 1, W, sh);
+    const int ng = (int)s.wpref[W];
+    for (int w = tid; w < W; w += K3_THREADS) {
+        uint32_t bits = s.start[w];
+        int idx = (int)s.wpref[w];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            s.slist[idx++] = (uint32_t)(w * 32 + b);
+        }
+    }
+    if (tid == 0) { s.slist[ng] = (uint32_t)nb; sh.ng = ng; }
+    __syncthreads();
+    uint32_t lmax = 0;
+    for (int g = tid; g < ng; g += K3_THREADS) {
+        const uint32_t s0 = s.slist[g], s1 = s.slist[g + 1];
+        const uint32_t sz = s.P[s1 - 1] - (s0 ? s.P[s0 - 1] : 0u);
+        s.gsize[g] = sz;
+        lmax = max(lmax, sz);
+    }
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xFFFFFFFFu, lmax, o));
+    if (lane == 0 && lmax) atomicMax(&sh.gmax, lmax);
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t k3_group_size(const K3Scratch& s, int b) {
+    const int w = b >> 5;
+    const int g = (int)s.wpref[w] + __popc(s.start[w] & (0xFFFFFFFFu >> (31 - (b & 31)))) - 1;
+    return s.gsize[g];
+}
+
+__device__ __forceinline__ void k3_zero(uint32_t* a, int n) {
+    for (int i = threadIdx.x; i < n; i += K3_THREADS) a[i] = 0;
+}
+
+struct PlotView {
+    uint2* hits;
+    uint32_t H;
+    int n, m;            // bins: d = y - x + (m-1) in [0, n+m-2], a = x + y in [0, n+m-2]
+};
+
+struct PlotStat {
+    uint32_t nclean;
+    unsigned long long sumabs;     // sum |x-y| over clean dots                (ABS)
+    uint32_t cnt10;                // eu_dis_dots_within_10perc over clean dots (W10)
+    double dir;                    // |eu_dis_dir_calcu| after re-centring      (REDEF)
+};
+
+// pass 0: span of x over all hits + checksum of the hit list
+__device__ void k3_pass0(const PlotView& v, K3Shared& sh, int& minx, int& maxx, unsigned long long& csum) {
+    if (threadIdx.x == 0) { sh.imin = 0x7FFFFFFF; sh.imax = -1; sh.u64a = 0; }
+    __syncthreads();
+    int lmin = 0x7FFFFFFF, lmax = -1;
+    unsigned long long lsum = 0;
+    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
+        const uint2 h = v.hits[i];
+        const int x = (int)h.x;
+        lmin = min(lmin, x); lmax = max(lmax, x);
+        lsum += hit_mix(h.x, h.y & HIT_Y_MASK);
+    }
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xFFFFFFFFu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xFFFFFFFFu, lmax, o));
+        lsum += __shfl_xor_sync(0xFFFFFFFFu, lsum, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&sh.imin, lmin); atomicMax(&sh.imax, lmax); atomicAdd(&sh.u64a, lsum);
+    }
+    __syncthreads();
+    minx = sh.imin; maxx = sh.imax; csum = sh.u64a;
+    __syncthreads();
+}
+
+// clean_dotdata_diagnal_and_anti_diagnal (Simple_function.pyx:432-448): keep a dot unless its y-x
+// chain group and its y+x chain group both have <= 10 members.  Sets HIT_F_CLEAN; returns count and
+// sum |x-y| of the kept dots.
+__device__ void k3_clean_a6(const PlotView& v, K3Scratch& s, K3Shared& sh, PlotStat& st) {
+    const int nb = v.n + v.m - 1;
+    k3_zero(s.P, nb);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
+        const uint2 h = v.hits[i];
+        atomicAdd(&s.P[(int)(h.y & HIT_Y_MASK) - (int)h.x + v.m - 1], 1u);
+    }
+    __syncthreads();
+    k3_build_groups(s, nb, sh);
+    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
+        uint2 h = v.hits[i];
+        const uint32_t y = h.y & HIT_Y_MASK;
+        const bool keep = k3_group_size(s, (int)y - (int)h.x + v.m - 1) > 10u;
+        v.hits[i].y = y | (keep ? HIT_F_KEEP1 : 0u);
+    }
+    __syncthreads();
+    k3_zero(s.P, nb);
+    if (threadIdx.x == 0) { sh.u32a = 0; sh.u64a = 0; }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
+        const uint2 h = v.hits[i];
+        atomicAdd(&s.P[(int)(h.y & HIT_Y_MASK) + (int)h.x], 1u);
+    }
+    __syncthreads();
+    k3_build_groups(s, nb, sh);
+    uint32_t lcnt = 0; unsigned long long lsum = 0;
+    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
+        uint2 h = v.hits[i];
+        const uint32_t y = h.y & HIT_Y_MASK;
+        const bool keep = (h.y & HIT_F_KEEP1) || k3_group_size(s, (int)y + (int)h.x) > 10u;
+        v.hits[i].y = y | (keep ? HIT_F_CLEAN : 0u);
+        if (keep) { ++lcnt; lsum += (unsigned long long)abs((int)h.x - (int)y); }
+    }
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lcnt += __shfl_xor_sync(0xFFFFFFFFu, lcnt, o);
+        lsum += __shfl_xor_sync(0xFFFFFFFFu, lsum, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sh.u32a, lcnt); atomicAdd(&sh.u64a, lsum); }
+    __syncthreads();
+    st.nclean = sh.u32a; st.sumabs = sh.u64a;
+    __syncthreads();
+}
+
+// dis_cluster keep rule (Simple_function.pyx:560-563): groups with > 50 members, or, when there is
+// none, every group tied for the maximum size.
+__device__ __forceinline__ bool k3_a7_keep(uint32_t sz, uint32_t gmax) {
+    return gmax > 50u ? sz > 50u : sz == gmax;
+}
+
+// W10 cleaning (Simple_function.pyx:281-288): dis_cluster on y-x, then dis_cluster on y+x over the
+// dots the first step did not keep; union.  Returns count and the within-16% count.
+__device__ void k3_clean_w10(const PlotView& v, K3Scratch& s, K3Shared& sh, PlotStat& st) {
+    st.nclean = 0; st.cnt10 = 0;
+    if (v.H == 0) return;                               // uniform across the block
+    const int nb = v.n + v.m - 1;
+    k3_zero(s.P, nb);
+    if (threadIdx.x == 0) { sh.u32a = 0; sh.u32b = 0; sh.u32c = 0; }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
+        const uint2 h = v.hits[i];
+        atomicAdd(&s.P[(int)(h.y & HIT_Y_MASK) - (int)h.x + v.m - 1], 1u);
+    }
+    __syncthreads();
+    k3_build_groups(s, nb, sh);
+    const uint32_t gmax1 = sh.gmax;
+    uint32_t lkept = 0;
+    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
+        uint2 h = v.hits[i];
+        const uint32_t y = h.y & HIT_Y_MASK;
+        const bool keep = k3_a7_keep(k3_group_size(s, (int)y - (int)h.x + v.m - 1), gmax1);
+        v.hits[i].y = y | (keep ? HIT_F_KEEP1 : 0u);
+        lkept += keep;
+    }
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) lkept += __shfl_xor_sync(0xFFFFFFFFu, lkept, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sh.u32a, lkept);
+    __syncthreads();
+    const uint32_t kept1 = sh.u32a;
+    const bool have_left = kept1 < v.H;
+    uint32_t gmax2 = 0;
+    if (have_left) {
+        k3_zero(s.P, nb);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
+            const uint2 h = v.hits[i];
+            if (!(h.y & HIT_F_KEEP1)) atomicAdd(&s.P[(int)(h.y & HIT_Y_MASK) + (int)h.x], 1u);
+        }
+        __syncthreads();
+        k3_build_groups(s, nb, sh);
+        gmax2 = sh.gmax;
+    }
+    uint32_t lcnt = 0, l10 = 0;
+    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
+        uint2 h = v.hits[i];
+        const uint32_t y = h.y & HIT_Y_MASK;
+        bool keep = (h.y & HIT_F_KEEP1) != 0;
+        if (!keep && have_left) keep = k3_a7_keep(k3_group_size(s, (int)y + (int)h.x), gmax2);
+        v.hits[i].y = y | (keep ? HIT_F_CLEAN : 0u);
+        if (keep) {
+            ++lcnt;
+            const int x = (int)h.x;
+            // abs(float(x-y)/float(x)) < 0.16 for x > 0  (Simple_function.pyx:732-733)
+            if (x > 0 && fabs((double)(x - (int)y) / (double)x) < 0.16) ++l10;
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lcnt += __shfl_xor_sync(0xFFFFFFFFu, lcnt, o);
+        l10 += __shfl_xor_sync(0xFFFFFFFFu, l10, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sh.u32b, lcnt); atomicAdd(&sh.u32c, l10); }
+    __syncthreads();
+    st.nclean = sh.u32b; st.cnt10 = sh.u32c;
+    __syncthreads();
+}
+
+// bin of value d among the 11 edges mn + i*(mx-mn)/10 as number_cluster assigns it
+// (Simple_function.pyx:1104-1118).  "d < mn + i*range/10.0" in doubles is exactly
+// "10*(d-mn) < i*range" in integers (kernel 3), so the bin is floor(10*(d-mn)/range),
+// and everything lands in the last bin when range == 0.
+__device__ __forceinline__ int k3_bin11(int d, int mn, int range) {
+    if (range <= 0) return 10;
+    return (int)((10ll * (long long)(d - mn)) / (long long)range);
+}
+
+// dis_to_diagnal_most_abundant_defined + eu_dis_dir_calcu on the clean dots (Simple_function.pyx:582-591,
+// 248-251, 710-722).  Needs HIT_F_CLEAN flags from k3_clean_a6 and st.nclean > 0.
+__device__ void k3_redef_stat(const PlotView& v, K3Scratch& s, K3Shared& sh, PlotStat& st) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int off = v.m - 1;
+    // level 1: range of d over the clean dots
+    if (tid == 0) { sh.imin = 0x7FFFFFFF; sh.imax = -0x7FFFFFFF; sh.icpt2 = 0; sh.sel = -1; }
+    if (tid < 11) sh.cnt11[tid] = 0;
+    __syncthreads();
+    int lmin = 0x7FFFFFFF, lmax = -0x7FFFFFFF;
+    for (uint32_t i = tid; i < v.H; i += K3_THREADS) {
+        const uint2 h = v.hits[i];
+        if (h.y & HIT_F_CLEAN) {
+            const int d = (int)(h.y & HIT_Y_MASK) - (int)h.x;
+            lmin = min(lmin, d); lmax = max(lmax, d);
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xFFFFFFFFu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xFFFFFFFFu, lmax, o));
+    }
+    if (lane == 0) { atomicMin(&sh.imin, lmin); atomicMax(&sh.imax, lmax); }
+    __syncthreads();
+    const int mn1 = sh.imin, rg1 = sh.imax - sh.imin;
+    for (uint32_t i = tid; i < v.H; i += K3_THREADS) {
+        const uint2 h = v.hits[i];
+        if (h.y & HIT_F_CLEAN) atomicAdd(&sh.cnt11[k3_bin11((int)(h.y & HIT_Y_MASK) - (int)h.x, mn1, rg1)], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {                                    // find_longest_list: exactly one modal bin?
+        unsigned best = 0; int nb = 0, bi = -1;
+        for (int b = 0; b < 11; ++b) best = max(best, sh.cnt11[b]);
+        for (int b = 0; b < 11; ++b) if (sh.cnt11[b] == best) { ++nb; bi = b; }
+        sh.sel = (nb == 1) ? bi : -1;
+        sh.m2min = 0x7FFFFFFF; sh.m2max = -0x7FFFFFFF;
+    }
+    __syncthreads();
+    const int b1 = sh.sel;
+    if (b1 >= 0) {                                     // uniform
+        // level 2 inside the modal bin
+        __syncthreads();
+        if (tid < 11) sh.cnt11[tid] = 0;
+        lmin = 0x7FFFFFFF; lmax = -0x7FFFFFFF;
+        for (uint32_t i = tid; i < v.H; i += K3_THREADS) {
+            const uint2 h = v.hits[i];
+            if (h.y & HIT_F_CLEAN) {
+                const int d = (int)(h.y & HIT_Y_MASK) - (int)h.x;
+                if (k3_bin11(d, mn1, rg1) == b1) { lmin = min(lmin, d); lmax = max(lmax, d); }
+            }
+        }
+        #pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lmin = min(lmin, __shfl_xor_sync(0xFFFFFFFFu, lmin, o));
+            lmax = max(lmax, __shfl_xor_sync(0xFFFFFFFFu, lmax, o));
+        }
+        if (lane == 0) { atomicMin(&sh.m2min, lmin); atomicMax(&sh.m2max, lmax); }
+        __syncthreads();
+        const int mn2 = sh.m2min, rg2 = sh.m2max - sh.m2min;
+        for (uint32_t i = tid; i < v.H; i += K3_THREADS) {
+            const uint2 h = v.hits[i];
+            if (h.y & HIT_F_CLEAN) {
+                const int d = (int)(h.y & HIT_Y_MASK) - (int)h.x;
+                if (k3_bin11(d, mn1, rg1) == b1) atomicAdd(&sh.cnt11[k3_bin11(d, mn2, rg2)], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned best = 0; int nb = 0, bj = -1;
+            for (int b = 0; b < 11; ++b) best = max(best, sh.cnt11[b]);
+            for (int b = 0; b < 11; ++b) if (sh.cnt11[b] == best) { ++nb; bj = b; }
+            sh.sel = (nb == 1) ? bj : -1;
+        }
+        __syncthreads();
+        const int b2 = sh.sel;
+        if (b2 >= 0) {                                 // uniform: np.median of that sub-bin
+            const uint32_t c = sh.cnt11[b2];
+            k3_zero(s.P, rg2 + 1);
+            __syncthreads();
+            for (uint32_t i = tid; i < v.H; i += K3_THREADS) {
+                const uint2 h = v.hits[i];
+                if (h.y & HIT_F_CLEAN) {
+                    const int d = (int)(h.y & HIT_Y_MASK) - (int)h.x;
+                    if (k3_bin11(d, mn1, rg1) == b1 && k3_bin11(d, mn2, rg2) == b2) atomicAdd(&s.P[d - mn2], 1u);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t r0 = (c - 1) / 2, r1 = c / 2;
+                uint32_t cum = 0; int v0 = -1, v1 = -1;
+                for (int t = 0; t <= rg2 && v1 < 0; ++t) {
+                    cum += s.P[t];
+                    if (v0 < 0 && cum > r0) v0 = t;
+                    if (cum > r1) v1 = t;
+                }
+                sh.icpt2 = (long long)(v0 + mn2) + (long long)(v1 + mn2);
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // eu_dis_dir_calcu on (x + intercept, y): in doubled integers A = 2(x'-y), B = 2x'
+    const long long icpt2 = sh.icpt2;
+    if (tid == 0) { sh.s64 = 0; sh.u32a = 0; }
+    __syncthreads();
+    long long lsum = 0; uint32_t lcnt = 0;
+    for (uint32_t i = tid; i < v.H; i += K3_THREADS) {
+        const uint2 h = v.hits[i];
+        if (h.y & HIT_F_CLEAN) {
+            const long long y = (long long)(h.y & HIT_Y_MASK);
+            const long long B = 2ll * (long long)h.x + icpt2;
+            const long long A = B - 2ll * y;
+            double ratio;
+            if (B == 0) ratio = fabs(((double)A * 0.5) / 1.0);       // x' == 0: divide by x'+1
+            else        ratio = fabs((double)A / (double)B);          // == (A/2)/(B/2) exactly
+            if (ratio > 0.1) { lsum += A; ++lcnt; }
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lsum += __shfl_xor_sync(0xFFFFFFFFu, lsum, o);
+        lcnt += __shfl_xor_sync(0xFFFFFFFFu, lcnt, o);
+    }
+    if (lane == 0) { atomicAdd((unsigned long long*)&sh.s64, (unsigned long long)lsum); atomicAdd(&sh.u32a, lcnt); }
+    __syncthreads();
+    if (sh.u32a == 0) st.dir = 0.0001;
+    else st.dir = fabs(((double)sh.s64 * 0.5) / (double)sh.u32a);
+    __syncthreads();
+}
+
+struct EvalResult {
+    double a, b;         // the [a, b] pair the reference function returns
+    bool valid;          // not (0 in pair)
+};
+
+__device__ __forceinline__ double k3_pair_score(const EvalResult& e) { return 1.0 - e.b / e.a; }
+
+struct K3Params {
+    const Task* tasks;
+    const int32_t* task_ids;     // tasks of this launch
+    int n_ids;
+    const Plot* plots;
+    const uint32_t* cnt;         // hits per plot
+    const int32_t* op_status;
+    uint2* hits;
+    uint32_t* gscratch;          // global scratch, [gridDim.x][scratch_words] (only when smem is too small)
+    int nb_cap;                  // bins the scratch can hold
+    int use_global;
+    double* task_score; uint8_t* task_status; double* task_stat; uint32_t* task_hits;
+    unsigned long long* task_hitsum;
+};
+
+// One evaluation of one reference mode on the (ref, alt) plots.  Block-uniform control flow.
+__device__ void k3_eval(int mode, const PlotView& pr, const PlotView& pa, int len_ref, int len_alt,
+                        K3Scratch& s, K3Shared& sh, EvalResult& out,
+                        unsigned long long& csr, unsigned long long& csa)
+{
+    int rminx, rmaxx, aminx, amaxx;
+    k3_pass0(pr, sh, rminx, rmaxx, csr);
+    k3_pass0(pa, sh, aminx, amaxx, csa);
+    out.a = 0; out.b = 0; out.valid = false;
+    const double Hr = (double)pr.H, Ha = (double)pa.H;
+    const double Lr = (double)len_ref, La = (double)len_alt;
+    PlotStat sr{}, sa{};
+    if (mode == 0) {                                   // ABS, Simple_function.pyx:187-203
+        if (!(pr.H > 2 && pa.H > 2)) return;
+        if (!(Hr / fmin(Lr, La) > 0.1)) return;
+        const bool rs = (double)(rmaxx - rminx) / Lr > 0.6;
+        const bool as = (double)(amaxx - aminx) / La > 0.6;
+        if (rs && as) {
+            k3_clean_a6(pr, s, sh, sr);
+            k3_clean_a6(pa, s, sh, sa);
+            if (sr.nclean > 0 && sa.nclean > 0) {
+                out.a = (double)sr.sumabs / (double)sr.nclean;      // np.mean of exact integers
+                out.b = (double)sa.sumabs / (double)sa.nclean;
+            }
+        } else if (rs) { out.a = 1.1; out.b = 2.1; }
+        else if (as)   { out.a = 2.1; out.b = 1.1; }
+    } else if (mode == 1) {                            // W10, Simple_function.pyx:280-294
+        if (!(fmax(Hr / Lr, Ha / La) > 0.1)) return;
+        k3_clean_w10(pr, s, sh, sr);
+        k3_clean_w10(pa, s, sh, sa);
+        if (sr.nclean > 0 && sa.nclean > 0) { out.a = (double)sa.cnt10; out.b = (double)sr.cnt10; }   // swapped on purpose (:290)
+    } else {                                           // REDEF, Simple_function.pyx:244-257
+        if (!(Hr / Lr > 0.1 && Ha / La > 0.1)) return;
+        if (!((double)(rmaxx - rminx) / Lr > 0.7 && (double)(amaxx - aminx) / La > 0.7)) return;
+        k3_clean_a6(pr, s, sh, sr);
+        k3_clean_a6(pa, s, sh, sa);
+        if (sr.nclean > 0 && sa.nclean > 0) {
+            k3_redef_stat(pr, s, sh, sr);
+            k3_redef_stat(pa, s, sh, sa);
+            out.a = sr.dir; out.b = sa.dir;
+        }
+    }
+    out.valid = (out.a != 0.0) && (out.b != 0.0);       // `if not 0 in pair`
+}
+
+__global__ void __launch_bounds__(K3_THREADS)
+k3_score_reads(const K3Params p)
+{
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    __shared__ K3Shared sh;
+    K3Scratch s;
+    k3_setup_scratch(s, p.use_global ? p.gscratch + (size_t)blockIdx.x * k3_scratch_words(p.nb_cap) : s_dyn, p.nb_cap);
+
+    for (int it = blockIdx.x; it < p.n_ids; it += gridDim.x) {
+        const int tix = p.task_ids[it];
+        const Task t = p.tasks[tix];
+        PlotView pv[4];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (t.plot[i] >= 0) {
+                const Plot pl = p.plots[t.plot[i]];
+                pv[i].hits = p.hits + pl.hit_off; pv[i].H = p.cnt[t.plot[i]]; pv[i].n = pl.n; pv[i].m = pl.m;
+            } else { pv[i].hits = nullptr; pv[i].H = 0; pv[i].n = 0; pv[i].m = 0; }
+        }
+        const bool bad = p.op_status[t.read_op] != 0;
+        EvalResult ea{0, 0, false}, eb{0, 0, false};
+        unsigned long long cs[4] = {0, 0, 0, 0};
+        if (!bad) {
+            const int modeA = (t.mode == 3) ? 0 : t.mode;
+            k3_eval(modeA, pv[0], pv[1], t.len_ref, t.len_alt, s, sh, ea, cs[0], cs[1]);
+            if (t.mode == 3) k3_eval(1, pv[2], pv[3], t.len_ref, t.len_alt, s, sh, eb, cs[2], cs[3]);
+        }
+        if (threadIdx.x == 0) {
+            double score = 0.0; uint8_t status = 0;
+            if (bad) status = 2;
+            else if (t.mode == 3) {                    // simple-DEL rule, Simple_function.pyx:1718-1726
+                if (ea.valid && eb.valid) { const double s1 = k3_pair_score(ea), s2 = k3_pair_score(eb); score = (s2 < s1) ? s2 : s1; status = 1; }
+                else if (ea.valid) { score = k3_pair_score(ea); status = 1; }
+                else if (eb.valid) { score = k3_pair_score(eb); status = 1; }
+            } else if (ea.valid) { score = k3_pair_score(ea); status = 1; }
+            p.task_score[tix] = score;
+            p.task_status[tix] = status;
+            p.task_stat[4 * tix + 0] = ea.a; p.task_stat[4 * tix + 1] = ea.b;
+            p.task_stat[4 * tix + 2] = eb.a; p.task_stat[4 * tix + 3] = eb.b;
+            for (int i = 0; i < 4; ++i) { p.task_hits[4 * tix + i] = pv[i].H; p.task_hitsum[4 * tix + i] = cs[i]; }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace vb
