@@ -166,7 +166,7 @@ int k3_class_of(int nb) {
 // planning: operands (k-mer word arrays), plots, tasks, waves
 // ------------------------------------------------------------------------------------------
 int plan_batch(Handle* h, const vapor_batch_t* in) {
-    if (!in || !in->seq_off || (!in->seq_bytes && in->n_seq > 0)) { h->err = "NULL batch arrays"; return VAPOR_E_ARG; }
+    if (!in || !in->seq_off || (!in->seq_bytes && in->n_seq > 0 && in->seq_off[in->n_seq] > 0)) { h->err = "NULL batch arrays"; return VAPOR_E_ARG; }
     if (in->n_task > 0 && (!in->task_read || !in->task_ref || !in->task_alt || !in->task_miss || !in->task_k || !in->task_mode)) {
         h->err = "NULL task arrays"; return VAPOR_E_ARG;
     }

@@ -198,6 +198,9 @@ class Engine:
     # -- lifecycle -------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
+            for p in getattr(self, "_pinned", []):
+                self._lib.vapor_gpu_host_free(p)
+            self._pinned = []
             self._lib.vapor_gpu_close(self._h)
             self._h = None
 
@@ -259,6 +262,48 @@ class Engine:
             if n.value <= cap:
                 return xy[:n.value]
             cap = int(n.value)
+
+    # -- pinned host staging ---------------------------------------------------------------
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array backed by page-locked host memory (``vapor_gpu_host_alloc``); freed on close()."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        nbytes = max(1, n * dtype.itemsize)
+        p = C.c_void_p()
+        rc = self._lib.vapor_gpu_host_alloc(C.byref(p), nbytes)
+        if rc != 0:
+            raise N.VaporNativeError(f"vapor_gpu_host_alloc({nbytes}) failed ({rc})")
+        if not hasattr(self, "_pinned"):
+            self._pinned = []
+        self._pinned.append(p)
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def pin_batch(self, batch: PackedBatch) -> PackedBatch:
+        """Copy a batch into pinned host memory so H2D copies run at full PCIe speed."""
+        out = {}
+        for f in batch.__dataclass_fields__:
+            a = getattr(batch, f)
+            b = self.pinned_empty(a.shape, a.dtype)
+            b[...] = a
+            out[f] = b
+        return PackedBatch(**out)
+
+    def pinned_results(self, n_task: int, n_sv: int) -> Results:
+        r = _alloc_results(n_task, n_sv)
+        for f in r.__dataclass_fields__:
+            a = getattr(r, f)
+            b = self.pinned_empty(a.shape, a.dtype)
+            b[...] = a
+            setattr(r, f, b)
+        return r
+
+    def score_into(self, batch: PackedBatch, res: Results) -> Results:
+        """``score`` writing into caller-provided (e.g. pinned) result arrays."""
+        b = batch.c_struct()
+        o = _out_struct(res)
+        self._check(self._lib.vapor_gpu_score(self._h, C.byref(b), C.byref(o)), "vapor_gpu_score")
+        return res
 
     def int_peak(self, which: int = 0) -> float:
         v = C.c_double(0)

@@ -150,84 +150,80 @@ class Workload:
     meta: Dict[str, object] = field(default_factory=dict)
 
 
+def _make_one_sv(args):
+    """Everything about SV ``i`` derives from ``default_rng([seed, i])``: any subset of a workload can be
+    regenerated on its own (the reference arm of bench.py scores a prefix of the same SV list)."""
+    (seed, i, types, size_range, reads_per_sv, err, het_frac, homref_frac, max_miss, lowercase_every, k_choices) = args
+    rng = np.random.default_rng([seed, i])
+    st = types[i % len(types)]
+    ln = int(rng.integers(size_range[0], size_range[1] + 1))
+    u = rng.random()
+    gt = 0 if u < homref_frac else (1 if u < homref_frac + het_frac else 2)
+    lc = 0.3 if (lowercase_every and i % lowercase_every == 0) else 0.0
+    case = make_sv_case(rng, st, ln, gt, k=int(k_choices[i % len(k_choices)]),
+                        micro_indel=bool(rng.random() < 0.12), lowercase_frac=lc)
+    if gt == 2:
+        from_alt = np.ones(reads_per_sv, dtype=bool)
+    elif gt == 1:
+        from_alt = rng.random(reads_per_sv) < 0.5
+    else:
+        from_alt = np.zeros(reads_per_sv, dtype=bool)
+    miss = rng.integers(0, max_miss + 1, size=reads_per_sv) if max_miss else np.zeros(reads_per_sv, dtype=np.int64)
+    want = case.read_window - miss
+    o_alt = len(case.hap_ref)
+    hap_len = np.where(from_alt, len(case.hap_alt), len(case.hap_ref))
+    need = np.minimum((want * 1.12).astype(np.int64) + 60, hap_len - miss)
+    start = np.where(from_alt, o_alt, 0) + miss
+    reads, roff = simulate_reads(rng, np.concatenate([case.hap_ref, case.hap_alt]), start, need, want, err=err)
+    lens = np.diff(roff)
+    n = np.maximum(lens - case.k + 1, 0)
+    m = np.maximum(len(case.ref_seq) - miss - case.k + 1, 0) + np.maximum(len(case.alt_seq) - miss - case.k + 1, 0)
+    return (st, ln, gt, case.ref_seq, case.alt_seq, reads, lens, miss.astype(np.int32), case.k, case.mode,
+            int((n * m).sum()))
+
+
 def make_workload(n_sv: int, seed: int = 20261018, types: Sequence[str] = SV_TYPES,
                   size_range: Tuple[int, int] = (50, 5000), reads_per_sv: int = 20, err: float = 0.15,
                   het_frac: float = 0.5, homref_frac: float = 0.1, max_miss: int = 0,
-                  lowercase_every: int = 0, k_choices: Sequence[int] = (10,), chunk_sv: int = 256) -> Workload:
-    """``n_sv`` simple SVs (types cycled, sizes uniform in ``size_range``), ``reads_per_sv`` reads each."""
-    rng = np.random.default_rng(seed)
+                  lowercase_every: int = 0, k_choices: Sequence[int] = (10,), workers: int = 0,
+                  first_sv: int = 0) -> Workload:
+    """SVs ``first_sv .. first_sv+n_sv-1`` of the seeded SV list (types cycled, sizes uniform in
+    ``size_range``), ``reads_per_sv`` reads each.  ``workers`` > 1 generates in that many processes."""
+    types = tuple(types); k_choices = tuple(k_choices)
+    jobs = [(seed, i, types, tuple(size_range), reads_per_sv, err, het_frac, homref_frac, max_miss,
+             lowercase_every, k_choices) for i in range(first_sv, first_sv + n_sv)]
+    if workers and workers > 1 and n_sv >= 4 * workers:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            outs = pool.map(_make_one_sv, jobs, chunksize=max(1, n_sv // (workers * 8)))
+    else:
+        outs = [_make_one_sv(j) for j in jobs]
     seq_parts: List[np.ndarray] = []
-    seq_lens: List[int] = []
-    t_read: List[np.ndarray] = []
-    t_ref: List[np.ndarray] = []
-    t_alt: List[np.ndarray] = []
-    t_miss: List[np.ndarray] = []
-    t_k: List[np.ndarray] = []
-    t_mode: List[np.ndarray] = []
-    sv_off = [0]
+    seq_lens: List[np.ndarray] = []
+    t_read, t_ref, t_alt, t_miss, t_k, t_mode = [], [], [], [], [], []
     sv_type: List[str] = []
     sv_len = np.zeros(n_sv, dtype=np.int64)
     sv_gt = np.zeros(n_sv, dtype=np.int8)
     cells = 0
     n_seq = 0
-    for c0 in range(0, n_sv, chunk_sv):
-        cases: List[SVCase] = []
-        for i in range(c0, min(n_sv, c0 + chunk_sv)):
-            st = types[i % len(types)]
-            ln = int(rng.integers(size_range[0], size_range[1] + 1))
-            u = rng.random()
-            gt = 0 if u < homref_frac else (1 if u < homref_frac + het_frac else 2)
-            lc = 0.3 if (lowercase_every and i % lowercase_every == 0) else 0.0
-            case = make_sv_case(rng, st, ln, gt, k=int(k_choices[i % len(k_choices)]),
-                                micro_indel=bool(rng.random() < 0.12), lowercase_frac=lc)
-            cases.append(case)
-            sv_type.append(st); sv_len[i] = ln; sv_gt[i] = gt
-        # one vectorised read simulation for the whole chunk
-        haps: List[np.ndarray] = []
-        hap_off = [0]
-        seg_start: List[int] = []
-        seg_len: List[int] = []
-        n_out: List[int] = []
-        miss_all: List[int] = []
-        for case in cases:
-            o_ref = hap_off[-1]; haps.append(case.hap_ref); hap_off.append(o_ref + len(case.hap_ref))
-            o_alt = hap_off[-1]; haps.append(case.hap_alt); hap_off.append(o_alt + len(case.hap_alt))
-            for _ in range(reads_per_sv):
-                from_alt = (case.genotype == 2) or (case.genotype == 1 and rng.random() < 0.5)
-                miss = int(rng.integers(0, max_miss + 1)) if max_miss else 0
-                want = case.read_window - miss
-                need = int(want * 1.12) + 60
-                hap_len = len(case.hap_alt) if from_alt else len(case.hap_ref)
-                need = min(need, hap_len - miss)
-                seg_start.append((o_alt if from_alt else o_ref) + miss)
-                seg_len.append(need); n_out.append(want); miss_all.append(miss)
-        reads, roff = simulate_reads(rng, np.concatenate(haps), np.array(seg_start), np.array(seg_len),
-                                     np.array(n_out), err=err)
-        ri = 0
-        for case in cases:
-            ref_id, alt_id = n_seq, n_seq + 1
-            seq_parts += [case.ref_seq, case.alt_seq]; seq_lens += [len(case.ref_seq), len(case.alt_seq)]
-            n_seq += 2
-            ids = np.arange(n_seq, n_seq + reads_per_sv, dtype=np.int32)
-            n_seq += reads_per_sv
-            seq_parts.append(reads[roff[ri]:roff[ri + reads_per_sv]])
-            lens = np.diff(roff[ri:ri + reads_per_sv + 1])
-            seq_lens += [int(v) for v in lens]
-            miss = np.array(miss_all[ri:ri + reads_per_sv], dtype=np.int32)
-            ri += reads_per_sv
-            t_read.append(ids)
-            t_ref.append(np.full(reads_per_sv, ref_id, np.int32)); t_alt.append(np.full(reads_per_sv, alt_id, np.int32))
-            t_miss.append(miss)
-            t_k.append(np.full(reads_per_sv, case.k, np.uint8)); t_mode.append(np.full(reads_per_sv, case.mode, np.uint8))
-            sv_off.append(sv_off[-1] + reads_per_sv)
-            n = np.maximum(lens - case.k + 1, 0)
-            m = np.maximum(len(case.ref_seq) - miss - case.k + 1, 0) + np.maximum(len(case.alt_seq) - miss - case.k + 1, 0)
-            cells += int((n * m).sum())
-    seq_off = np.zeros(len(seq_lens) + 1, dtype=np.int64)
-    np.cumsum(np.array(seq_lens, dtype=np.int64), out=seq_off[1:])
-    batch = PackedBatch(np.concatenate(seq_parts), seq_off, np.concatenate(t_read), np.concatenate(t_ref),
-                        np.concatenate(t_alt), np.concatenate(t_miss), np.concatenate(t_k), np.concatenate(t_mode),
-                        np.array(sv_off, dtype=np.int64)).validate()
+    for j, (st, ln, gt, ref, alt, reads, lens, miss, k, mode, c) in enumerate(outs):
+        sv_type.append(st); sv_len[j] = ln; sv_gt[j] = gt; cells += c
+        seq_parts += [ref, alt, reads]
+        seq_lens.append(np.concatenate([[len(ref), len(alt)], lens]).astype(np.int64))
+        ids = np.arange(n_seq + 2, n_seq + 2 + reads_per_sv, dtype=np.int32)
+        t_read.append(ids)
+        t_ref.append(np.full(reads_per_sv, n_seq, np.int32)); t_alt.append(np.full(reads_per_sv, n_seq + 1, np.int32))
+        t_miss.append(miss)
+        t_k.append(np.full(reads_per_sv, k, np.uint8)); t_mode.append(np.full(reads_per_sv, mode, np.uint8))
+        n_seq += 2 + reads_per_sv
+    seq_off = np.zeros(n_seq + 1, dtype=np.int64)
+    if seq_lens:
+        np.cumsum(np.concatenate(seq_lens), out=seq_off[1:])
+    sv_off = np.arange(n_sv + 1, dtype=np.int64) * reads_per_sv
+    cat = lambda parts, dt: (np.concatenate(parts) if parts else np.zeros(0, dt))
+    batch = PackedBatch(cat(seq_parts, np.uint8), seq_off, cat(t_read, np.int32), cat(t_ref, np.int32),
+                        cat(t_alt, np.int32), cat(t_miss, np.int32), cat(t_k, np.uint8), cat(t_mode, np.uint8),
+                        sv_off).validate()
     return Workload(batch, sv_type, sv_len, sv_gt, np.full(n_sv, reads_per_sv, np.int32), cells,
                     {"seed": seed, "types": list(types), "size_range": list(size_range), "err": err,
-                     "reads_per_sv": reads_per_sv})
+                     "reads_per_sv": reads_per_sv, "first_sv": first_sv})
