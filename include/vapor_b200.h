@@ -138,6 +138,13 @@ int vapor_gpu_dotdata(void* handle, int k, const uint8_t* read, int64_t read_len
                       const uint8_t* structure, int64_t struct_len,
                       int32_t* xy, int64_t cap, int64_t* n_hits);
 
+/* Per-SV summary + genotype alone, for score lists that already sit on the host: kernel 4 on
+ * scores[sv_off[s] .. sv_off[s+1]) for every SV s.  Replaces result_organize_ins (Simple_function.pyx:1219-1231)
+ * and gt_estimate_log_likelihood (Simple_function.pyx:2054-2069) when the CLI calls them on a driver's
+ * vapor_score_list (vapor_vali/vapor:339-340).  Outputs as in vapor_out_t. */
+int vapor_gpu_summarize(void* handle, const double* scores, const int64_t* sv_off, int64_t n_sv,
+                        double* sv_qs, double* sv_gs, double* sv_gq, uint8_t* sv_gt, int32_t* sv_nscore);
+
 /* Pinned host memory for staging (optional; any host pointer is accepted by score/upload). */
 int vapor_gpu_host_alloc(void** p, int64_t bytes);
 int vapor_gpu_host_free(void* p);

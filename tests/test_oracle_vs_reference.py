@@ -1,0 +1,91 @@
+"""Differential tests: the numpy oracle against the live, unmodified reference module.  Only runs where
+/root/reference (or its compiled copy oracle/_ref) is available -- i.e. in the build container."""
+import numpy as np
+import pytest
+
+from oracle import batch_oracle as BO
+from oracle import vapor_oracle as O
+from oracle.reference_loader import load_reference
+from vapor_b200 import synth
+
+R = load_reference()
+pytestmark = pytest.mark.skipif(R is None, reason="reference module not available on this machine")
+
+MODES = ["calcu_vapor_single_read_score_abs_dis_m1b", "calcu_vapor_single_read_score_within_10Perc_m1b",
+         "calcu_vapor_single_read_score_directed_dis_m1b_redefine_diagnal"]
+
+
+def _mk(rng, st, ln, k, err, lower):
+    case = synth.make_sv_case(rng, st, ln, genotype=1, k=k, lowercase_frac=lower)
+    hap = case.hap_alt if rng.random() < 0.5 else case.hap_ref
+    miss = int(rng.integers(0, 4))
+    want = case.read_window - miss
+    reads, _ = synth.simulate_reads(rng, hap, np.array([miss]), np.array([min(len(hap) - miss, int(want * 1.12) + 60)]),
+                                    np.array([want]), err=err)
+    return reads.tobytes().decode(), case.ref_seq.tobytes().decode(), case.alt_seq.tobytes().decode(), miss
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_modes_random(seed):
+    rng = np.random.default_rng(100 + seed)
+    branches = set()
+    for it in range(10):
+        st = synth.SV_TYPES[it % 4]
+        k = (10, 10, 20, 30, 40)[it % 5]
+        read, ref, alt, miss = _mk(rng, st, int(rng.integers(50, 1200)), k, 0.15 if k == 10 else 0.05,
+                                   0.3 if it % 4 == 0 else 0.0)
+        d1 = np.array(R.dotdata(k, read, ref[miss:]), dtype=np.int64).reshape(-1, 2)
+        d2 = O.dotdata(k, read, ref[miss:])
+        assert np.array_equal(d1, d2)
+        for m in MODES:
+            a = getattr(R, m)(ref, alt, [read, miss, "q"], k)
+            b = getattr(O, m)(ref, alt, [read, miss, "q"], k)
+            assert float(a[0]) == float(b[0]) and float(a[1]) == float(b[1]), (m, a, b)
+            branches.add((m, 0 in a, a[0] in (1.1, 2.1)))
+    assert len(branches) >= 4
+
+
+def test_unrelated_and_truncated_reads():
+    rng = np.random.default_rng(5)
+    ref = synth.random_dna(rng, 1200).tobytes().decode()
+    alt = ref[:500] + ref[700:]
+    for read in (synth.random_dna(rng, 900).tobytes().decode(), ref[:300], ref[200:1100], alt[:400]):
+        for m in MODES:
+            a = getattr(R, m)(ref, alt, [read, 0, "q"], 10)
+            b = getattr(O, m)(ref, alt, [read, 0, "q"], 10)
+            assert [float(a[0]), float(a[1])] == [float(b[0]), float(b[1])]
+
+
+def test_batch_oracle_matches_reference_drivers_rule():
+    """score_batch with impl=reference == impl=oracle (per-read combine, SV summaries)."""
+    w = synth.make_workload(6, seed=77, size_range=(50, 700), reads_per_sv=5, max_miss=2, lowercase_every=3)
+    a = BO.score_batch(w.batch, impl=R, with_hits=False)
+    b = BO.score_batch(w.batch, impl=O, with_hits=False)
+    for key in ("task_score", "task_status", "task_stat", "sv_qs", "sv_gs", "sv_gt", "sv_nscore"):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.allclose(a["sv_gq"], b["sv_gq"], rtol=0, atol=1e-12)
+    assert a["sv_rec"] == b["sv_rec"]
+
+
+def test_summaries_random():
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        n = int(rng.integers(1, 150))
+        sc = [float(v) for v in rng.uniform(-2, 1, n)]
+        ra = R.result_organize_ins(["k", sc]); rb = O.result_organize_ins(["k", sc])
+        assert float(ra[1]) == float(rb[1]) and ra[2:] == rb[2:]
+        ga = R.gt_estimate_log_likelihood(ra); gb = O.gt_estimate_log_likelihood(rb)
+        assert ga[0] == gb[0] and abs(float(ga[1]) - float(gb[1])) < 1e-12
+
+
+try:
+    from hypothesis import given, settings, strategies as st_
+
+    @settings(max_examples=60, deadline=None)
+    @given(st_.text(alphabet="ACGTNacgtnRY", min_size=0, max_size=60), st_.text(alphabet="ACGTNacgtnRYX", min_size=0, max_size=80),
+           st_.sampled_from([2, 4, 6, 10]))
+    def test_dotdata_property(read, struct, k):
+        d1 = np.array(R.dotdata(k, read, struct), dtype=np.int64).reshape(-1, 2)
+        assert np.array_equal(d1, O.dotdata(k, read, struct))
+except ImportError:      # pragma: no cover
+    pass

@@ -20,7 +20,7 @@ VAPOR_OK, VAPOR_E_CUDA, VAPOR_E_ARG, VAPOR_E_CAPACITY, VAPOR_E_STATE = 0, -1, -2
 EXPORTS = [
     "vapor_gpu_open", "vapor_gpu_close", "vapor_gpu_last_error", "vapor_gpu_set_hit_budget",
     "vapor_gpu_score", "vapor_gpu_upload", "vapor_gpu_run", "vapor_gpu_fetch",
-    "vapor_gpu_last_timings", "vapor_gpu_dotdata", "vapor_gpu_host_alloc", "vapor_gpu_host_free",
+    "vapor_gpu_last_timings", "vapor_gpu_dotdata", "vapor_gpu_summarize", "vapor_gpu_host_alloc", "vapor_gpu_host_free",
     "vapor_gpu_int_peak", "vapor_hit_mix", "vapor_b200_abi_version",
 ]
 
@@ -91,15 +91,12 @@ def load() -> C.CDLL:
     lib.vapor_gpu_fetch.argtypes = [vp, C.POINTER(vapor_out_t)]
     lib.vapor_gpu_last_timings.argtypes = [vp, C.POINTER(vapor_timings_t)]
     lib.vapor_gpu_dotdata.argtypes = [vp, i32, vp, i64, vp, i64, vp, i64, C.POINTER(i64)]
+    lib.vapor_gpu_summarize.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
     lib.vapor_gpu_host_alloc.argtypes = [C.POINTER(vp), i64]
     lib.vapor_gpu_host_free.argtypes = [vp]
     lib.vapor_gpu_int_peak.argtypes = [vp, i32, C.POINTER(C.c_double)]
     lib.vapor_hit_mix.argtypes = [C.c_uint32, C.c_uint32]
     lib.vapor_hit_mix.restype = C.c_uint64
     lib.vapor_b200_abi_version.argtypes = []
-    for name in EXPORTS:
-        fn = getattr(lib, name)
-        if fn.restype is C.c_int or name in ("vapor_gpu_last_error", "vapor_hit_mix"):
-            continue
     _lib = lib
     return lib

@@ -754,6 +754,38 @@ int vapor_gpu_dotdata(void* handle, int k, const uint8_t* read, int64_t read_len
     return VAPOR_OK;
 }
 
+int vapor_gpu_summarize(void* handle, const double* scores, const int64_t* sv_off, int64_t n_sv,
+                        double* sv_qs, double* sv_gs, double* sv_gq, uint8_t* sv_gt, int32_t* sv_nscore)
+{
+    if (!handle) return VAPOR_E_ARG;
+    Handle* h = static_cast<Handle*>(handle);
+    if (n_sv < 0 || (n_sv > 0 && !sv_off)) { h->err = "bad summarize arguments"; return VAPOR_E_ARG; }
+    if (n_sv == 0) return VAPOR_OK;
+    const int64_t n = sv_off[n_sv];
+    if (sv_off[0] != 0 || n < 0 || (n > 0 && !scores)) { h->err = "bad summarize arguments"; return VAPOR_E_ARG; }
+    CK(cudaSetDevice(h->device));
+    h->resident = false; h->ran = false;            // the task buffers are reused
+    const size_t nt = (size_t)n, nsv = (size_t)n_sv;
+    CK(h->d_task_score.ensure(nt + 1)); CK(h->d_task_status.ensure(nt + 1)); CK(h->d_pos.ensure(nt + 1));
+    CK(h->d_sv_off.ensure(nsv + 1));
+    CK(h->d_sv_qs.ensure(nsv + 1)); CK(h->d_sv_gs.ensure(nsv + 1)); CK(h->d_sv_gq.ensure(nsv + 1));
+    CK(h->d_sv_gt.ensure(nsv + 1)); CK(h->d_sv_nscore.ensure(nsv + 1));
+    if (nt) CK(cudaMemcpyAsync(h->d_task_score.p, scores, nt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_task_status.p, 1, nt + 1, h->stream));
+    CK(cudaMemcpyAsync(h->d_sv_off.p, sv_off, (nsv + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    k4_genotype<<<(unsigned)((nsv + 127) / 128), 128, 0, h->stream>>>(
+        h->d_sv_off.p, (int)nsv, h->d_task_score.p, h->d_task_status.p, h->d_pos.p,
+        h->d_sv_qs.p, h->d_sv_gs.p, h->d_sv_gq.p, h->d_sv_gt.p, h->d_sv_nscore.p);
+    CK(cudaGetLastError());
+    if (sv_qs) CK(cudaMemcpyAsync(sv_qs, h->d_sv_qs.p, nsv * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (sv_gs) CK(cudaMemcpyAsync(sv_gs, h->d_sv_gs.p, nsv * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (sv_gq) CK(cudaMemcpyAsync(sv_gq, h->d_sv_gq.p, nsv * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (sv_gt) CK(cudaMemcpyAsync(sv_gt, h->d_sv_gt.p, nsv, cudaMemcpyDeviceToHost, h->stream));
+    if (sv_nscore) CK(cudaMemcpyAsync(sv_nscore, h->d_sv_nscore.p, nsv * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return VAPOR_OK;
+}
+
 int vapor_gpu_host_alloc(void** p, int64_t bytes) {
     if (!p || bytes < 0) return VAPOR_E_ARG;
     cudaError_t e = cudaMallocHost(p, (size_t)std::max<int64_t>(bytes, 1));

@@ -320,7 +320,6 @@ __device__ __forceinline__ int k3_bin11(int d, int mn, int range) {
 // 248-251, 710-722).  Needs HIT_F_CLEAN flags from k3_clean_a6 and st.nclean > 0.
 __device__ void k3_redef_stat(const PlotView& v, K3Scratch& s, K3Shared& sh, PlotStat& st) {
     const int tid = threadIdx.x, lane = tid & 31;
-    const int off = v.m - 1;
     // level 1: range of d over the clean dots
     if (tid == 0) { sh.imin = 0x7FFFFFFF; sh.imax = -0x7FFFFFFF; sh.icpt2 = 0; sh.sel = -1; }
     if (tid < 11) sh.cnt11[tid] = 0;

@@ -263,6 +263,21 @@ class Engine:
                 return xy[:n.value]
             cap = int(n.value)
 
+    def summarize(self, score_lists):
+        """QS/GS/GT/GQ for a list of per-SV score lists (kernel 4 alone, ``vapor_gpu_summarize``).
+        Returns arrays (qs, gs, gq, gt, nscore); gt == 255 marks the reference's 'NA' row."""
+        n_sv = len(score_lists)
+        off = np.zeros(n_sv + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in score_lists], out=off[1:])
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.float64) for s in score_lists])
+                                    if n_sv and off[-1] else np.zeros(0), dtype=np.float64)
+        qs = np.zeros(n_sv); gs = np.zeros(n_sv); gq = np.zeros(n_sv)
+        gt = np.full(n_sv, 255, np.uint8); ns = np.zeros(n_sv, np.int32)
+        rc = self._lib.vapor_gpu_summarize(self._h, flat.ctypes.data if len(flat) else None, off.ctypes.data, n_sv,
+                                           qs.ctypes.data, gs.ctypes.data, gq.ctypes.data, gt.ctypes.data, ns.ctypes.data)
+        self._check(rc, "vapor_gpu_summarize")
+        return qs, gs, gq, gt, ns
+
     # -- pinned host staging ---------------------------------------------------------------
     def pinned_empty(self, shape, dtype) -> np.ndarray:
         """numpy array backed by page-locked host memory (``vapor_gpu_host_alloc``); freed on close()."""
