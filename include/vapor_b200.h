@@ -102,6 +102,7 @@ typedef struct vapor_timings {
     int64_t n_plots, n_operands, n_strips, n_waves, n_overflow_plots;
     int64_t launches;            /* kernels launched by the last run                     */
     int64_t bases;               /* bases packed by kernel 1                             */
+    int64_t padded_cells;        /* cells the tile kernel evaluates, strip padding included */
 } vapor_timings_t;
 
 /* Open one handle on CUDA device `device`.  One handle per device/thread; a handle is
@@ -113,6 +114,10 @@ const char* vapor_gpu_last_error(void* handle);   /* handle may be NULL: last op
 
 /* Tunables: hit-buffer budget in bytes (0 = default) -- bounds device memory per wave. */
 int vapor_gpu_set_hit_budget(void* handle, int64_t bytes);
+/* Named tunables (none changes a result): "hit_budget_bytes", "tile_variant" (inner loop of the tile
+ * kernel: 0 = 16 rows/lane by ISETP only, 1 = 14 by ISETP + 2 row polynomials by IMAD [default],
+ * 2 = 16 + 2 polynomials), "k2_ctas_per_sm" (persistent-grid size).  Takes effect at the next upload. */
+int vapor_gpu_set_option(void* handle, const char* name, int64_t value);
 
 /* Blocking one-shot: host prep + H2D + kernels 1-4 + D2H.
  * Replaces the read loops `for x in all_reads: calcu_vapor_single_read_score_*(...)`
@@ -137,6 +142,15 @@ int vapor_gpu_last_timings(void* handle, vapor_timings_t* t);
 int vapor_gpu_dotdata(void* handle, int k, const uint8_t* read, int64_t read_len,
                       const uint8_t* structure, int64_t struct_len,
                       int32_t* xy, int64_t cap, int64_t* n_hits);
+
+/* Self-plot quality control of window_size_refine (Simple_function.pyx:2030-2046): for every sequence i the
+ * recurrence plot dotdata(k[i], seq_i, seq_i) is evaluated by kernels 1-2 and reduced on the fly to the
+ * counts qual_check_repetitive_region (Simple_function.pyx:1154-1171) needs; no hit list is stored.
+ * out[8*i ..]: len(dotdata), hits with x == y, hits with x > y, then min x, max x, min y, max y over the
+ * x > y hits (0xFFFFFFFF / 0 when there is none), and VAPOR_ST_SCORED or VAPOR_ST_BADREAD (the sequence
+ * holds a character invert_base rejects: the reference raises KeyError). */
+int vapor_gpu_selfplot_qc(void* handle, const uint8_t* seq_bytes, const int64_t* seq_off, int64_t n_seq,
+                          const uint8_t* k, int64_t* out);
 
 /* Per-SV summary + genotype alone, for score lists that already sit on the host: kernel 4 on
  * scores[sv_off[s] .. sv_off[s+1]) for every SV s.  Replaces result_organize_ins (Simple_function.pyx:1219-1231)

@@ -142,3 +142,35 @@ def test_hit_budget_waves_identical(engine):
         small.close()
     for f in base.__dataclass_fields__:
         np.testing.assert_array_equal(getattr(res, f), getattr(base, f))
+
+
+def test_selfplot_qc_counts(engine):
+    """vapor_gpu_selfplot_qc against the counts qual_check_repetitive_region takes from dotdata(k, s, s)
+    (Simple_function.pyx:1154-1171), on random, repetitive, palindromic and N-holding windows."""
+    rng = np.random.default_rng(17)
+    seqs, ks = [], []
+    base = synth.random_dna(rng, 2600)
+    seqs.append(base); ks.append(10)
+    rep = np.concatenate([base[:700], base[200:700], base[200:700], base[700:1500]])      # tandem repeats
+    seqs.append(rep); ks.append(10)
+    seqs.append(rep); ks.append(20)
+    seqs.append(rep); ks.append(40)
+    inv = np.concatenate([base[:900], synth.revcomp(base[300:900]), base[900:1200]])       # inverted repeat
+    seqs.append(inv); ks.append(10)
+    withn = base[:1500].copy(); withn[300:350] = ord("N")
+    seqs.append(withn); ks.append(10)
+    seqs.append(np.frombuffer(b"ACGTACGTACGTACGTACGTACGTACGT", dtype=np.uint8)); ks.append(4)   # palindromic k-mers
+    seqs.append(np.frombuffer(b"ACGTA", dtype=np.uint8)); ks.append(10)                    # shorter than k
+    seqs.append(synth.random_dna(rng, 6000)); ks.append(10)                                # several strips, transposed tail
+    got = engine.selfplot_qc(seqs, ks)
+    for i, (s, k) in enumerate(zip(seqs, ks)):
+        st = s.tobytes().decode()
+        d = O.dotdata(k, st, st)
+        low = d[d[:, 0] > d[:, 1]]
+        exp = [len(d), int((d[:, 0] == d[:, 1]).sum()), len(low)]
+        assert got[i, :3].tolist() == exp, (i, k)
+        if len(low):
+            assert got[i, 3:7].tolist() == [low[:, 0].min(), low[:, 0].max(), low[:, 1].min(), low[:, 1].max()], i
+        assert got[i, 7] == 1
+    bad = base[:400].copy(); bad[77] = ord("X")
+    assert engine.selfplot_qc([bad], [10])[0, 7] == 2

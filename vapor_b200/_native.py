@@ -18,9 +18,9 @@ VAPOR_OK, VAPOR_E_CUDA, VAPOR_E_ARG, VAPOR_E_CAPACITY, VAPOR_E_STATE = 0, -1, -2
 
 # every symbol include/vapor_b200.h declares
 EXPORTS = [
-    "vapor_gpu_open", "vapor_gpu_close", "vapor_gpu_last_error", "vapor_gpu_set_hit_budget",
+    "vapor_gpu_open", "vapor_gpu_close", "vapor_gpu_last_error", "vapor_gpu_set_hit_budget", "vapor_gpu_set_option",
     "vapor_gpu_score", "vapor_gpu_upload", "vapor_gpu_run", "vapor_gpu_fetch",
-    "vapor_gpu_last_timings", "vapor_gpu_dotdata", "vapor_gpu_summarize", "vapor_gpu_host_alloc", "vapor_gpu_host_free",
+    "vapor_gpu_last_timings", "vapor_gpu_dotdata", "vapor_gpu_selfplot_qc", "vapor_gpu_summarize", "vapor_gpu_host_alloc", "vapor_gpu_host_free",
     "vapor_gpu_int_peak", "vapor_hit_mix", "vapor_b200_abi_version",
 ]
 
@@ -56,7 +56,7 @@ class vapor_timings_t(C.Structure):
         ("cells", C.c_int64), ("hits", C.c_int64),
         ("n_plots", C.c_int64), ("n_operands", C.c_int64), ("n_strips", C.c_int64),
         ("n_waves", C.c_int64), ("n_overflow_plots", C.c_int64),
-        ("launches", C.c_int64), ("bases", C.c_int64),
+        ("launches", C.c_int64), ("bases", C.c_int64), ("padded_cells", C.c_int64),
     ]
 
     def as_dict(self):
@@ -85,12 +85,14 @@ def load() -> C.CDLL:
     lib.vapor_gpu_last_error.argtypes = [vp]
     lib.vapor_gpu_last_error.restype = C.c_char_p
     lib.vapor_gpu_set_hit_budget.argtypes = [vp, i64]
+    lib.vapor_gpu_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.vapor_gpu_score.argtypes = [vp, C.POINTER(vapor_batch_t), C.POINTER(vapor_out_t)]
     lib.vapor_gpu_upload.argtypes = [vp, C.POINTER(vapor_batch_t)]
     lib.vapor_gpu_run.argtypes = [vp]
     lib.vapor_gpu_fetch.argtypes = [vp, C.POINTER(vapor_out_t)]
     lib.vapor_gpu_last_timings.argtypes = [vp, C.POINTER(vapor_timings_t)]
     lib.vapor_gpu_dotdata.argtypes = [vp, i32, vp, i64, vp, i64, vp, i64, C.POINTER(i64)]
+    lib.vapor_gpu_selfplot_qc.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.vapor_gpu_summarize.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
     lib.vapor_gpu_host_alloc.argtypes = [C.POINTER(vp), i64]
     lib.vapor_gpu_host_free.argtypes = [vp]

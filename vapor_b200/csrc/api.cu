@@ -80,6 +80,10 @@ struct Handle {
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t hit_budget = 0;          // bytes; 0 = default
+    int k2_ctas_per_sm = 0;          // persistent-grid size of kernel 2 = this x SM count; 0 = occupancy
+    int k2_occupancy[K2_NVARIANT] = {0, 0, 0};
+    int tile_variant = 1;            // k2 inner-loop variant (k2_variant_*), fixed at upload
+    int plan_variant = 1;            // variant the resident plan's strips were cut for
 
     // plan (host)
     std::vector<Operand> ops;
@@ -95,6 +99,7 @@ struct Handle {
     int64_t hash_elems = 0, code_bytes = 0, max_wave_hits = 0;
     bool resident = false, ran = false;
     vapor_timings_t tm{};
+    int64_t tm_padded_cells = 0;     // cells the tile kernel evaluates including strip padding
 
     // device
     DevBuf<uint8_t> d_seq, d_code, d_task_status, d_sv_gt;
@@ -103,7 +108,7 @@ struct Handle {
     DevBuf<Task> d_tasks;
     DevBuf<int32_t> d_chunk_prefix, d_op_status, d_class_ids, d_sv_nscore, d_ovf_ids;
     DevBuf<int64_t> d_strip_prefix, d_sv_off, d_ovf_prefix;
-    DevBuf<uint32_t> d_hash, d_cnt, d_task_hits, d_gscratch, d_misc;
+    DevBuf<uint32_t> d_hash, d_cnt, d_task_hits, d_gscratch, d_misc, d_qc;
     DevBuf<uint2> d_hits, d_ovf_hits;
     DevBuf<double> d_task_score, d_task_stat, d_pos, d_sv_qs, d_sv_gs, d_sv_gq;
     DevBuf<unsigned long long> d_task_hitsum, d_queue;
@@ -156,6 +161,25 @@ void build_lut() {
 }
 
 inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
+
+// Cut one plot into strips for the tile kernel (see k2_tile.cuh): sets kind/n_main_strips, returns the strip count.
+int64_t cut_strips(Plot& p, int rows, int64_t* padded_cells) {
+    p.kind &= ~PLOT_TAIL_T; p.n_main_strips = 0;
+    if (p.n <= 0 || p.m <= 0) return 0;
+    const int n_full = p.n / rows, t = p.n % rows;
+    const int ncol = (p.m + K2_TS - 1) / K2_TS;
+    p.n_main_strips = n_full * ncol;
+    int64_t strips = p.n_main_strips;
+    if (padded_cells) *padded_cells += (int64_t)n_full * rows * ((p.m + 31) & ~31);
+    if (t > 0) {
+        const int64_t c_n = k2_cells_padded_tail(rows, t, p.m, false), c_t = k2_cells_padded_tail(rows, t, p.m, true);
+        const bool tr = c_t < c_n;
+        if (tr) p.kind |= PLOT_TAIL_T;
+        strips += k2_tail_strips(rows, t, p.m, tr);
+        if (padded_cells) *padded_cells += tr ? c_t : c_n;
+    }
+    return strips;
+}
 
 int k3_class_of(int nb) {
     for (int c = 0; c < K3_NCLASS - 1; ++c) if (nb <= k3_class_cap[c]) return c;
@@ -269,12 +293,12 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
     const int64_t budget_bytes = h->hit_budget > 0 ? h->hit_budget : (int64_t)6 << 30;
     const int64_t budget_elems = std::max<int64_t>(budget_bytes / (int64_t)sizeof(uint2), 1 << 16);
     h->strip_prefix.assign(h->plots.size() + 1, 0);
+    h->plan_variant = h->tile_variant;
+    int64_t padded_cells = 0;
     for (size_t i = 0; i < h->plots.size(); ++i) {
-        const Plot& p = h->plots[i];
-        int64_t strips = (p.n > 0 && p.m > 0)
-            ? (int64_t)((p.n + K2_ROWS - 1) / K2_ROWS) * (int64_t)((p.m + K2_TS - 1) / K2_TS) : 0;
-        h->strip_prefix[i + 1] = h->strip_prefix[i] + strips;
+        h->strip_prefix[i + 1] = h->strip_prefix[i] + cut_strips(h->plots[i], k2_variant_rows(h->plan_variant), &padded_cells);
     }
+    h->tm_padded_cells = padded_cells;
     h->max_nb = 1; h->max_wave_hits = 0;
     {
         Wave w{0, 0, 0, 0, 0};
@@ -326,6 +350,7 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
     h->hash_elems = hash_off + 16; h->code_bytes = code_off + 64;
     h->tm = vapor_timings_t{};
     h->tm.cells = cells; h->tm.n_plots = (int64_t)h->plots.size(); h->tm.n_operands = (int64_t)h->ops.size();
+    h->tm.padded_cells = h->tm_padded_cells;
     h->tm.n_strips = h->strip_prefix.back(); h->tm.n_waves = (int64_t)h->waves.size(); h->tm.bases = bases;
     return VAPOR_OK;
 }
@@ -382,6 +407,27 @@ int upload_impl(Handle* h, const vapor_batch_t* in) {
 
 namespace {
 
+// persistent grid: one CTA per resident CTA slot (occupancy x SM count), strips pulled from the queue
+template <int V>
+void launch_k2_variant(Handle* h, const K2Params& kp) {
+    auto kern = k2_tile_match<k2_variant_ni(V), k2_variant_np(V)>;
+    if (h->k2_occupancy[V] == 0) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K2_THREADS, 0) != cudaSuccess || occ < 1) occ = 4;
+        h->k2_occupancy[V] = occ;
+    }
+    const int per_sm = h->k2_ctas_per_sm > 0 ? h->k2_ctas_per_sm : h->k2_occupancy[V];
+    const int grid = (int)std::min<int64_t>((kp.n_strips + K2_WARPS - 1) / K2_WARPS, (int64_t)h->sm_count * per_sm);
+    kern<<<grid, K2_THREADS, 0, h->stream>>>(kp);
+}
+void launch_k2(Handle* h, const K2Params& kp) {
+    switch (h->plan_variant) {
+        case 0:  launch_k2_variant<0>(h, kp); break;
+        case 2:  launch_k2_variant<2>(h, kp); break;
+        default: launch_k2_variant<1>(h, kp); break;
+    }
+}
+
 int run_impl(Handle* h) {
     if (!h->resident) { h->err = "no resident batch: call vapor_gpu_upload first"; return VAPOR_E_STATE; }
     CK(cudaSetDevice(h->device));
@@ -427,9 +473,7 @@ int run_impl(Handle* h) {
             kp.cnt = h->d_cnt.p + w.plot_begin;
             kp.queue = h->d_queue.p;
             kp.overflow = h->d_misc.p;
-            const int64_t warps_needed = n_strips;
-            int grid = (int)std::min<int64_t>((warps_needed + K2_WARPS - 1) / K2_WARPS, (int64_t)h->sm_count * 8);
-            k2_tile_match<<<grid, K2_THREADS, 0, h->stream>>>(kp);
+            launch_k2(h, kp);
             ++launches;
         }
         span_end(h, sp);
@@ -482,8 +526,7 @@ int run_impl(Handle* h) {
             kp.n_plots = (int)re_plots.size(); kp.n_strips = re_prefix.back(); kp.strip_base = 0;
             kp.hash = h->d_hash.p; kp.code = h->d_code.p; kp.hits = h->d_hits.p;
             kp.cnt = d_recnt.p; kp.queue = h->d_queue.p; kp.overflow = h->d_misc.p;
-            int grid = (int)std::min<int64_t>((kp.n_strips + K2_WARPS - 1) / K2_WARPS, (int64_t)h->sm_count * 8);
-            k2_tile_match<<<grid, K2_THREADS, 0, h->stream>>>(kp);
+            launch_k2(h, kp);
             ++launches;
             span_end(h, sp);
             CK(cudaGetLastError());
@@ -669,7 +712,7 @@ int vapor_gpu_close(void* handle) {
     h->d_ops.release(); h->d_plots.release(); h->d_tasks.release();
     h->d_chunk_prefix.release(); h->d_op_status.release(); h->d_class_ids.release(); h->d_sv_nscore.release(); h->d_ovf_ids.release();
     h->d_strip_prefix.release(); h->d_sv_off.release(); h->d_ovf_prefix.release();
-    h->d_hash.release(); h->d_cnt.release(); h->d_task_hits.release(); h->d_gscratch.release(); h->d_misc.release();
+    h->d_hash.release(); h->d_cnt.release(); h->d_task_hits.release(); h->d_gscratch.release(); h->d_misc.release(); h->d_qc.release();
     h->d_hits.release(); h->d_ovf_hits.release();
     h->d_task_score.release(); h->d_task_stat.release(); h->d_pos.release(); h->d_sv_qs.release(); h->d_sv_gs.release(); h->d_sv_gq.release();
     h->d_task_hitsum.release(); h->d_queue.release();
@@ -684,6 +727,24 @@ int vapor_gpu_set_hit_budget(void* handle, int64_t bytes) {
     if (!handle) return VAPOR_E_ARG;
     static_cast<Handle*>(handle)->hit_budget = bytes;
     return VAPOR_OK;
+}
+
+int vapor_gpu_set_option(void* handle, const char* name, int64_t value) {
+    if (!handle || !name) return VAPOR_E_ARG;
+    Handle* h = static_cast<Handle*>(handle);
+    const std::string n(name);
+    if (n == "hit_budget_bytes") { h->hit_budget = value; return VAPOR_OK; }
+    if (n == "tile_variant") {
+        if (value < 0 || value >= K2_NVARIANT) { h->err = "tile_variant out of range"; return VAPOR_E_ARG; }
+        h->tile_variant = (int)value; h->resident = false; h->ran = false;       // strips must be re-cut
+        return VAPOR_OK;
+    }
+    if (n == "k2_ctas_per_sm") {
+        if (value < 0 || value > 32) { h->err = "k2_ctas_per_sm out of range"; return VAPOR_E_ARG; }
+        h->k2_ctas_per_sm = (int)value; return VAPOR_OK;
+    }
+    h->err = "unknown option: " + n;
+    return VAPOR_E_ARG;
 }
 
 int vapor_gpu_upload(void* handle, const vapor_batch_t* in) {
@@ -751,6 +812,82 @@ int vapor_gpu_dotdata(void* handle, int k, const uint8_t* read, int64_t read_len
     std::sort(hits.begin(), hits.end(), [](const uint2& a, const uint2& b2) { return a.x != b2.x ? a.x < b2.x : a.y < b2.y; });
     const int64_t nw = std::min<int64_t>(cap, cnt);
     for (int64_t i = 0; i < nw; ++i) { xy[2 * i] = (int32_t)hits[i].x; xy[2 * i + 1] = (int32_t)hits[i].y; }
+    return VAPOR_OK;
+}
+
+int vapor_gpu_selfplot_qc(void* handle, const uint8_t* seq_bytes, const int64_t* seq_off, int64_t n_seq,
+                          const uint8_t* k, int64_t* out)
+{
+    if (!handle) return VAPOR_E_ARG;
+    Handle* h = static_cast<Handle*>(handle);
+    if (n_seq < 0 || (n_seq > 0 && (!seq_off || !k || !out))) { h->err = "bad selfplot_qc arguments"; return VAPOR_E_ARG; }
+    if (n_seq == 0) return VAPOR_OK;
+    const int64_t total = seq_off[n_seq];
+    if (seq_off[0] != 0 || total < 0 || (total > 0 && !seq_bytes)) { h->err = "bad selfplot_qc arguments"; return VAPOR_E_ARG; }
+    CK(cudaSetDevice(h->device));
+    h->resident = false; h->ran = false;                       // plan and device buffers are reused
+    // one read-role operand per sequence serves both axes of its self-plot
+    std::vector<Operand> ops((size_t)n_seq);
+    std::vector<Plot> plots((size_t)n_seq);
+    std::vector<int32_t> chunk_prefix((size_t)n_seq + 1, 0);
+    std::vector<int64_t> strip_prefix((size_t)n_seq + 1, 0);
+    const int k2_rows = k2_variant_rows(h->tile_variant);
+    int64_t hash_off = 0, code_off = 0;
+    for (int64_t i = 0; i < n_seq; ++i) {
+        const int64_t L = seq_off[i + 1] - seq_off[i];
+        if (L < 0 || L >= (1ll << 27)) { h->err = "sequence length out of range (0 .. 2^27)"; return VAPOR_E_ARG; }
+        if (k[i] < 1 || k[i] > K1_MAXK) { h->err = "window_size k must be 1..40"; return VAPOR_E_ARG; }
+        Operand o{};
+        o.seq_begin = seq_off[i]; o.len = (int32_t)L; o.k = k[i]; o.flags = OPF_READ;
+        o.n = std::max(0, o.len - o.k + 1);
+        o.hash_off = hash_off; o.code_off = code_off;
+        hash_off += align4(o.n) + 8; code_off += o.len + 8;
+        ops[i] = o;
+        Plot p{};
+        p.read_op = p.struct_op = (int32_t)i; p.miss = 0; p.n = p.m = o.n; p.cap = 0; p.kind = PLOT_QC; p.hit_off = i;
+        strip_prefix[i + 1] = strip_prefix[i] + cut_strips(p, k2_rows, nullptr);
+        plots[i] = p;
+        chunk_prefix[i + 1] = chunk_prefix[i] + std::max(1, (o.len + K1_CHUNK - 1) / K1_CHUNK);
+    }
+    h->plan_variant = h->tile_variant;
+    const size_t ns = (size_t)n_seq;
+    CK(h->d_seq.ensure((size_t)total + 64)); CK(h->d_ops.ensure(ns + 1)); CK(h->d_plots.ensure(ns + 1));
+    CK(h->d_chunk_prefix.ensure(ns + 1)); CK(h->d_strip_prefix.ensure(ns + 1));
+    CK(h->d_hash.ensure((size_t)hash_off + 16)); CK(h->d_code.ensure((size_t)code_off + 64));
+    CK(h->d_op_status.ensure(ns + 1)); CK(h->d_cnt.ensure(ns + 1)); CK(h->d_qc.ensure(ns * QC_WORDS));
+    CK(h->d_queue.ensure(4)); CK(h->d_misc.ensure(16));
+    if (total > 0) CK(cudaMemcpyAsync(h->d_seq.p, seq_bytes, (size_t)total, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_ops.p, ops.data(), ns * sizeof(Operand), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_plots.p, plots.data(), ns * sizeof(Plot), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_chunk_prefix.p, chunk_prefix.data(), (ns + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_strip_prefix.p, strip_prefix.data(), (ns + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    std::vector<uint32_t> qc_init(ns * QC_WORDS, 0u);
+    for (size_t i = 0; i < ns; ++i) { qc_init[i * QC_WORDS + 3] = 0xFFFFFFFFu; qc_init[i * QC_WORDS + 5] = 0xFFFFFFFFu; }
+    CK(cudaMemcpyAsync(h->d_qc.p, qc_init.data(), qc_init.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_op_status.p, 0, (ns + 1) * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(h->d_cnt.p, 0, (ns + 1) * sizeof(uint32_t), h->stream));
+    CK(cudaMemsetAsync(h->d_queue.p, 0, 4 * sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(h->d_misc.p, 0, 16 * sizeof(uint32_t), h->stream));
+    k1_pack_kmers<<<chunk_prefix.back(), K1_THREADS, 0, h->stream>>>(
+        h->d_seq.p, h->d_ops.p, h->d_chunk_prefix.p, (int)ns, h->d_hash.p, h->d_code.p, h->d_op_status.p);
+    CK(cudaGetLastError());
+    if (strip_prefix.back() > 0) {
+        K2Params kp{};
+        kp.plots = h->d_plots.p; kp.ops = h->d_ops.p; kp.strip_prefix = h->d_strip_prefix.p;
+        kp.n_plots = (int)ns; kp.n_strips = strip_prefix.back(); kp.strip_base = 0;
+        kp.hash = h->d_hash.p; kp.code = h->d_code.p; kp.hits = nullptr; kp.cnt = h->d_cnt.p;
+        kp.queue = h->d_queue.p; kp.overflow = h->d_misc.p; kp.qc = h->d_qc.p;
+        launch_k2(h, kp);
+        CK(cudaGetLastError());
+    }
+    std::vector<int32_t> st(ns);
+    CK(cudaMemcpyAsync(qc_init.data(), h->d_qc.p, qc_init.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(st.data(), h->d_op_status.p, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < ns; ++i) {
+        for (int j = 0; j < 7; ++j) out[i * 8 + j] = (int64_t)qc_init[i * QC_WORDS + j];
+        out[i * 8 + 7] = st[i] ? VAPOR_ST_BADREAD : VAPOR_ST_SCORED;
+    }
     return VAPOR_OK;
 }
 

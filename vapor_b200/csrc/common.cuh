@@ -9,11 +9,17 @@ namespace vb {
 // codes: A0 C1 G2 T3 N4  a8 c9 g10 t11 n12, IUPAC RYSWKMBDHV -> N(4) / n(12), anything else 15.
 constexpr int CODE_INVALID = 15;
 
-// ---- k-mer hash sentinels --------------------------------------------------------------
+// ---- k-mer words -------------------------------------------------------------------------
+// bit 31: the word is a hash, not injective -- a match must be confirmed on the code strings
+// bit 30: the k-mer is its own reverse complement (the reference appends such a dot twice)
+// bits 0..29: exact canonical code (mixed) or hash.  No valid word is >= 0xFFFFFFFC.
+constexpr uint32_t H_NEEDS_VERIFY   = 0x80000000u;
+constexpr uint32_t H_PALINDROME     = 0x40000000u;
 constexpr uint32_t H_STRUCT_INVALID = 0xFFFFFFFFu;  // structure k-mer that can never match (holds 'X', ...)
-constexpr uint32_t H_READ_PAD       = 0xFFFFFFFEu;  // read padding / rejected read k-mer
-constexpr uint32_t H_MAX_VALID      = 0xFFFFFFFDu;
-constexpr uint32_t H_NEEDS_VERIFY   = 0x80000000u;  // bit 31: hash is not injective, confirm on the code strings
+constexpr uint32_t H_READ_PAD       = 0xFFFFFFFEu;  // rejected read k-mer (the read's status is BADREAD)
+constexpr uint32_t H_STREAM_PAD     = 0xFFFFFFFDu;  // tile kernel: padding of the streamed (shared-memory) axis
+constexpr uint32_t H_ROW_PAD        = 0xFFFFFFFCu;  // tile kernel: padding of the register (row) axis
+constexpr uint32_t H_MAX_VALID      = 0xFFFFFFFBu;
 
 // operand flags
 constexpr int OPF_UPPER = 1;   // str.upper() applied (ABS mode upper-cases ref/alt, Simple_function.pyx:183-184)
@@ -35,7 +41,16 @@ struct Plot {              // one recurrence plot: read operand x structure oper
     int32_t miss;          // structure is cut [miss:]
     int32_t n, m;          // read k-mers, structure k-mers after the cut
     uint32_t cap;          // capacity of the hit list
+    int32_t kind;          // PLOT_QC bit: count into qc[hit_off*QC_WORDS ...] instead of appending hits at hit_off;
+                           // PLOT_TAIL_T bit: the last (partial) read chunk is tiled transposed (see k2_tile.cuh)
+    int32_t n_main_strips; // strips of the full read chunks; the tail strips follow
 };
+constexpr int PLOT_QC = 1, PLOT_TAIL_T = 2;
+
+// Self-plot quality-control counters of one PLOT_QC plot (window_size_refine / qual_check_repetitive_region,
+// Simple_function.pyx:2030-2046, 1154-1171): all hits, hits on the diagonal, hits below it (x > y) and
+// the bounding box of those.
+constexpr int QC_WORDS = 8;      // H, diag, lower, min x, max x, min y, max y (of the lower hits), spare
 
 struct Task {              // one read of one SV/allele
     int32_t plot[4];       // ref, alt of evaluation A; ref, alt of the W10 evaluation of ABS_AND_W10 (else -1)

@@ -7,11 +7,13 @@
 //
 // Per operand this kernel writes
 //   code[i]  : 4-bit alphabet code of base i (| 0x80 when the k-mer starting at i is its own
-//              reverse complement -> the reference appends the same position twice), and
-//   hash[i]  : 32-bit canonical k-mer word.  For k <= 15 and a pure ACGT k-mer the word is the
-//              exact canonical 2-bit code (< 2^30, injective: no confirmation needed); otherwise
+//              reverse complement), and
+//   hash[i]  : 32-bit canonical k-mer word.  For k <= 15 and a pure ACGT k-mer the word is a
+//              bijective mix of the exact canonical 2-bit code (< 2^30, injective: no confirmation
+//              needed); otherwise
 //              bit 31 is set and the word is a symmetric hash of (forward, revcomp) that the
-//              tile kernel confirms on the code strings.
+//              tile kernel confirms on the code strings.  Bit 30 marks a k-mer that is its own
+//              reverse complement: the reference appends such a read position twice.
 // HBM-bound: 1 B/base read, 1 B/base + 4 B/position written.
 #pragma once
 #include "common.cuh"
@@ -29,6 +31,16 @@ __device__ __forceinline__ uint64_t fmix64(uint64_t z) {
     z ^= z >> 33; z *= 0xC4CEB9FE1A85EC53ull;
     z ^= z >> 33;
     return z;
+}
+
+// Bijection on [0, 2^30): exact words stay exact (equal iff the canonical k-mers are equal) while their
+// low bits stop being "the last bases of the k-mer" -- the tile kernel's row polynomials live in
+// Z/2^32 and give a false candidate when differences share many trailing zero bits.
+__host__ __device__ __forceinline__ uint32_t mix30(uint32_t x) {
+    x ^= x >> 15; x = (x * 0x2C1B3C6Du) & 0x3FFFFFFFu;
+    x ^= x >> 12; x = (x * 0x297A2D39u) & 0x3FFFFFFFu;
+    x ^= x >> 15;
+    return x;
 }
 
 __global__ void __launch_bounds__(K1_THREADS)
@@ -87,7 +99,7 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
                     r = (r << 2) | (uint32_t)(3 - s_code[i + k - 1 - t]);
                 }
                 pal = (f == r);
-                h = min(f, r);
+                h = mix30(min(f, r)) | (pal ? H_PALINDROME : 0u);
             } else {
                 const uint64_t B = 0x9E3779B97F4A7C15ull | 1ull;
                 uint64_t f = 0, r = 0;
@@ -102,9 +114,9 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
                         pal &= (s_code[i + t] == comp_code(s_code[i + k - 1 - t]));
                 }
                 uint64_t cmin = f < r ? f : r, cmax = f < r ? r : f;
-                uint32_t h31 = (uint32_t)(fmix64(cmin ^ (cmax * 0xD6E8FEB86659FD93ull)) >> 33);
-                h = H_NEEDS_VERIFY | h31;
-                if (h > H_MAX_VALID) h -= 2;
+                uint32_t h30 = (uint32_t)(fmix64(cmin ^ (cmax * 0xD6E8FEB86659FD93ull)) >> 34);
+                h = H_NEEDS_VERIFY | (pal ? H_PALINDROME : 0u) | h30;
+                if (h > H_MAX_VALID) h -= 4;
             }
             hash[op.hash_off + base0 + i] = h;
         }

@@ -4,27 +4,57 @@
 // dot (i, j) when the strings are equal forward or reverse-complemented
 // (vapor_vali/Simple_function.pyx:964-979), a self-reverse-complement read k-mer emitting it
 // twice (:959-960, :1419-1421).  The reference gets there with a Python dict; this kernel
-// evaluates every cell of the n x m plot with one 32-bit compare on canonical k-mer words and
-// never materialises the matrix: only the sparse hit list reaches HBM.
+// evaluates every cell of the n x m plot on 32-bit canonical k-mer words and never materialises
+// the matrix: only the sparse hit list reaches HBM.
 //
-// Decomposition: a *strip* is 32*R consecutive read k-mers (R per lane, in registers) against
-// K2_TS consecutive structure k-mers staged in shared memory by a 1-D TMA bulk copy
-// (cp.async.bulk + mbarrier, one buffer per warp, no block-wide barrier anywhere).  Each warp
-// of a persistent grid pulls strips from a global queue.  The inner loop is R compares per
-// broadcast shared-memory word, OR-accumulated into predicates; a warp vote every 32
-// structure k-mers sends the rare blocks that hold a match to a warp-cooperative slow path
-// that locates, confirms (hash words with bit 31 set) and appends the hits.
+// Decomposition: a *strip* is 32*R consecutive k-mer words of one axis (R per lane, in registers:
+// the "rows") against up to K2_TS consecutive words of the other axis staged in shared memory by a
+// 1-D TMA bulk copy (cp.async.bulk + mbarrier, one buffer per warp, no block-wide barrier
+// anywhere: the "stream").  Each warp of a persistent grid pulls strips from a global queue.
+// Equality is symmetric, so either axis can be the rows: the full read chunks of a plot take the
+// read k-mers as rows and stream the structure; the last, partial read chunk is tiled transposed
+// (structure k-mers as rows, the few left-over read k-mers streamed) when that wastes fewer padded
+// cells -- the host decides per plot (PLOT_TAIL_T).
+//
+// Inner loop, dual pipe.  B200 issues integer compares (ISETP) on the alu pipe and integer
+// multiply-adds (IMAD) on the fma pipe, each at 64 lanes/clk/SM (tools/microbench2.cu).  A lane's
+// R = NI + 8*NP rows are therefore split: NI rows are compared one ISETP each, and every further
+// group of 8 rows is folded into the monic polynomial P(v) = prod_q (v - r_q) mod 2^32, evaluated
+// for each structure word v by Horner's rule (8 fma-pipe ops) and tested against zero once.
+// P(v) == 0 whenever v equals one of the 8 rows (no false negatives); a zero without a match needs
+// the factors' trailing zero bits to sum to >= 32 (about 3.5e-5 per evaluation on mixed words) and
+// only costs a visit to the exact path.  A warp vote every 32 structure k-mers sends the blocks
+// that hold a candidate to a warp-cooperative exact path that locates, confirms (hash words with
+// bit 31 set are checked on the code strings) and appends the hits.
 #pragma once
 #include "common.cuh"
 
 namespace vb {
 
-constexpr int K2_R       = 16;                 // read k-mers per lane
-constexpr int K2_ROWS    = 32 * K2_R;          // read k-mers per strip
-constexpr int K2_TS      = 2048;               // structure k-mers per strip
+constexpr int K2_D       = 8;                  // rows folded into one polynomial
+constexpr int K2_TS      = 2048;               // streamed k-mers per strip
 constexpr int K2_WARPS   = 4;                  // warps per CTA
 constexpr int K2_THREADS = 32 * K2_WARPS;
 constexpr int K2_SBUF    = K2_TS + 40;         // words per warp buffer (alignment shift + vote-block padding)
+
+// tile variants: (rows by ISETP, row polynomials).  Variant 1 is the product default.
+constexpr int K2_NVARIANT = 3;
+__host__ __device__ constexpr int k2_variant_ni(int v) { return v == 0 ? 16 : (v == 1 ? 14 : 16); }
+__host__ __device__ constexpr int k2_variant_np(int v) { return v == 0 ? 0 : 2; }
+__host__ __device__ constexpr int k2_variant_rows(int v) { return 32 * (k2_variant_ni(v) + K2_D * k2_variant_np(v)); }
+
+// Strips of one plot (host and device agree through these two functions).
+// Full read chunks first: strip = (read chunk rc, structure chunk cc), rc fastest.  Then the tail chunk
+// of t = n % rows read k-mers: either as one more read chunk (ceil(m / K2_TS) strips) or transposed
+// (ceil(m / rows) strips of structure rows, the t read k-mers streamed; t < rows <= K2_TS).
+__host__ __device__ inline int64_t k2_cells_padded_tail(int rows, int t, int m, bool transposed) {
+    return transposed ? (int64_t)((m + rows - 1) / rows) * rows * ((t + 31) & ~31)
+                      : (int64_t)rows * ((m + 31) & ~31);
+}
+__host__ __device__ inline int k2_tail_strips(int rows, int t, int m, bool transposed) {
+    if (t == 0) return 0;
+    return transposed ? (m + rows - 1) / rows : (m + K2_TS - 1) / K2_TS;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -52,7 +82,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 
 // Confirm a candidate on the code strings: structure k-mer == read k-mer, forward or reverse-complemented.
-__device__ __forceinline__ bool verify_kmer(const uint8_t* __restrict__ cr, const uint8_t* __restrict__ cs, int k) {
+__device__ __noinline__ bool verify_kmer(const uint8_t* __restrict__ cr, const uint8_t* __restrict__ cs, int k) {
     bool fwd = true, rev = true;
     for (int t = 0; t < k; ++t) {
         int s = cs[t] & 15;
@@ -75,11 +105,31 @@ struct K2Params {
     uint32_t* cnt;              // [n_plots] hits found (may exceed cap)
     unsigned long long* queue;  // strip queue head
     uint32_t* overflow;         // set when any plot exceeded its capacity
+    uint32_t* qc;               // [n_qc_plots * QC_WORDS] counters of PLOT_QC plots (may be null when there is none)
 };
 
-__global__ void __launch_bounds__(K2_THREADS)
+// Exact path, step 1: for candidate lane L and its rows Q0, Q0+STEP, ... (NQ of them), lane t of the warp
+// (holding streamed word v) marks the rows of L whose word equals v.  Rows are fetched by shuffle.
+template <int Q0, int NQ, int STEP, int R>
+__device__ __forceinline__ uint32_t k2_match_rows(const uint32_t (&r)[R], int L, uint32_t v)
+{
+    uint32_t hm = 0;
+    #pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        const int q = Q0 + i * STEP;
+        const uint32_t rq = __shfl_sync(0xFFFFFFFFu, r[q], L);
+        if (rq == v) hm |= 1u << q;
+    }
+    return hm;
+}
+
+template <int NI, int NP>
+__global__ void __launch_bounds__(K2_THREADS, 5)
 k2_tile_match(const K2Params p)
 {
+    constexpr int R = NI + K2_D * NP;              // rows per lane; row q of lane l is strip row q*32 + l
+    constexpr int ROWS = 32 * R;
+    static_assert(NI % 2 == 0 && NP <= 2 && R <= 32, "row split");
     __shared__ __align__(16) uint32_t s_buf[K2_WARPS][K2_SBUF];
     __shared__ __align__(8) uint64_t s_bar[K2_WARPS];
 
@@ -108,91 +158,150 @@ k2_tile_match(const K2Params p)
         }
         const Plot pl = p.plots[lo];
         const int local = (int)(strip - (unsigned long long)(p.strip_prefix[lo] - p.strip_base));
-        const int n_rc = (pl.n + K2_ROWS - 1) / K2_ROWS;
-        const int rc = local % n_rc;             // read chunk fastest: neighbours share the structure chunk in L2
-        const int cc = local / n_rc;
         const Operand opr = p.ops[pl.read_op];
         const Operand ops_ = p.ops[pl.struct_op];
+        const long long read_words = opr.hash_off;                   // element index of read k-mer 0
+        const long long struct_words = ops_.hash_off + pl.miss;      // element index of structure k-mer 0 (after the cut)
 
-        // ---- stage the structure words with one TMA bulk copy ------------------------------------
-        const int x0 = cc * K2_TS;
-        const int valid = min(K2_TS, pl.m - x0);
-        const long long src_elem = ops_.hash_off + pl.miss + x0;
-        const int shift = (int)(src_elem & 3);                       // TMA wants 16-byte aligned source
-        const uint32_t bytes = (uint32_t)(((shift + valid + 3) & ~3) * 4);
+        // ---- decode the strip: which words are rows (registers), which are streamed (shared memory) ----
+        const int n_full = pl.n / ROWS;                              // full read chunks
+        bool swap = false;                                           // true: rows = structure k-mers, stream = read k-mers
+        long long rows_elem, stream_elem;
+        int rows_valid, stream_valid, row0, stream0;                 // row0/stream0: coordinate of the first row / streamed word
+        if (local < pl.n_main_strips) {
+            const int rc = local % n_full, cc = local / n_full;      // read chunk fastest: neighbours share the structure chunk in L2
+            row0 = rc * ROWS; rows_valid = ROWS; rows_elem = read_words + row0;
+            stream0 = cc * K2_TS; stream_valid = min(K2_TS, pl.m - stream0); stream_elem = struct_words + stream0;
+        } else {
+            const int lt = local - pl.n_main_strips;
+            const int t0 = n_full * ROWS, t = pl.n - t0;             // the tail read chunk
+            if (pl.kind & PLOT_TAIL_T) {
+                swap = true;
+                row0 = lt * ROWS; rows_valid = min(ROWS, pl.m - row0); rows_elem = struct_words + row0;
+                stream0 = t0; stream_valid = t; stream_elem = read_words + t0;
+            } else {
+                row0 = t0; rows_valid = t; rows_elem = read_words + t0;
+                stream0 = lt * K2_TS; stream_valid = min(K2_TS, pl.m - stream0); stream_elem = struct_words + stream0;
+            }
+        }
+
+        // ---- stage the streamed words with one TMA bulk copy ---------------------------------------
+        const int shift = (int)(stream_elem & 3);                    // TMA wants a 16-byte aligned source
+        const uint32_t bytes = (uint32_t)(((shift + stream_valid + 3) & ~3) * 4);
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic writes to sb
             mbar_expect_tx(bar, bytes);
-            tma_bulk_g2s(sb, p.hash + (src_elem - shift), bytes, bar);
+            tma_bulk_g2s(sb, p.hash + (stream_elem - shift), bytes, bar);
         }
 
-        // ---- read words into registers while the copy is in flight -------------------------------
-        uint32_t r[K2_R];
-        const int ybase = rc * K2_ROWS + lane * K2_R;
+        // ---- row words into registers (coalesced: row q of lane l = strip row q*32+l) ---------------
+        uint32_t r[R];
         {
-            const uint32_t* rh = p.hash + opr.hash_off + ybase;
+            const uint32_t* rh = p.hash + rows_elem + lane;
+            const int left = rows_valid - lane;                      // row q of this lane exists while q*32 < left
             #pragma unroll
-            for (int q = 0; q < K2_R; q += 4) {
-                if (ybase + q + 3 < pl.n) {
-                    uint4 v = *reinterpret_cast<const uint4*>(rh + q);
-                    r[q] = v.x; r[q + 1] = v.y; r[q + 2] = v.z; r[q + 3] = v.w;
-                } else {
+            for (int q = 0; q < R; ++q) r[q] = (q * 32 < left) ? rh[q * 32] : H_ROW_PAD;
+        }
+        // ---- row polynomials: P_g(v) = prod over the valid rows j of group g of (v - r[NI+8g+j]), as
+        //      c[g][0] v^8 + c[g][1] v^7 + ... + c[g][8].  Padding rows are left out of the product (their
+        //      common value would stack trailing zero bits and fake candidates). -------------------------
+        uint32_t c[NP > 0 ? NP : 1][K2_D + 1];
+        #pragma unroll
+        for (int g = 0; g < NP; ++g) {
+            uint32_t a[K2_D + 1];                                    // a[i] = coefficient of v^i
+            a[0] = 1u;
+            #pragma unroll
+            for (int i = 1; i <= K2_D; ++i) a[i] = 0u;
+            #pragma unroll
+            for (int j = 0; j < K2_D; ++j) {
+                const uint32_t w = r[NI + K2_D * g + j];
+                if (w != H_ROW_PAD) {
                     #pragma unroll
-                    for (int e = 0; e < 4; ++e) r[q + e] = (ybase + q + e < pl.n) ? rh[q + e] : H_READ_PAD;
+                    for (int i = j + 1; i >= 1; --i) a[i] = a[i - 1] - w * a[i];
+                    a[0] = 0u - w * a[0];
                 }
             }
+            #pragma unroll
+            for (int i = 0; i <= K2_D; ++i) c[g][i] = a[K2_D - i];
         }
 
         mbar_wait(bar, parity);
         parity ^= 1;
-        const int nblk = (valid + 31) >> 5;
-        for (int i = shift + valid + lane; i < shift + nblk * 32; i += 32) sb[i] = H_STRUCT_INVALID;
+        // vote blocks start at the 16-byte aligned head of the buffer (LDS.128): the `shift` words in front of
+        // the chunk and the tail padding are overwritten with a word no row equals
+        const int nblk = (shift + stream_valid + 31) >> 5;
+        if (lane < shift) sb[lane] = H_STREAM_PAD;
+        for (int i = shift + stream_valid + lane; i < nblk * 32; i += 32) sb[i] = H_STREAM_PAD;
         __syncwarp();
 
-        const uint32_t* s = sb + shift;
         for (int b = 0; b < nblk; ++b) {
-            const uint32_t* sblk = s + b * 32;
-            bool p0 = false, p1 = false, p2 = false, p3 = false;
+            const uint32_t* sblk = sb + b * 32;
+            bool pi0 = false, pi1 = false, pg0 = false, pg1 = false;
             #pragma unroll
             for (int jj = 0; jj < 32; jj += 4) {
-                const uint32_t v0 = sblk[jj], v1 = sblk[jj + 1], v2 = sblk[jj + 2], v3 = sblk[jj + 3];
+                const uint4 v4 = *reinterpret_cast<const uint4*>(sblk + jj);
+                const uint32_t vw[4] = {v4.x, v4.y, v4.z, v4.w};
                 #pragma unroll
-                for (int q = 0; q < K2_R; ++q) {
-                    p0 |= (r[q] == v0);
-                    p1 |= (r[q] == v1);
-                    p2 |= (r[q] == v2);
-                    p3 |= (r[q] == v3);
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t v = vw[e];
+                    uint32_t acc[NP > 0 ? NP : 1];
+                    #pragma unroll
+                    for (int g = 0; g < NP; ++g) acc[g] = c[g][0] * v + c[g][1];
+                    #pragma unroll
+                    for (int i = 2; i <= K2_D; ++i)
+                        #pragma unroll
+                        for (int g = 0; g < NP; ++g) acc[g] = acc[g] * v + c[g][i];
+                    #pragma unroll
+                    for (int q = 0; q < NI; q += 2) { pi0 |= (r[q] == v); pi1 |= (r[q + 1] == v); }
+                    if (NP > 0) pg0 |= (acc[0] == 0u);
+                    if (NP > 1) pg1 |= (acc[NP > 1 ? 1 : 0] == 0u);
                 }
             }
-            unsigned mask = __ballot_sync(0xFFFFFFFFu, p0 | p1 | p2 | p3);
-            if (mask == 0) continue;
+            if (__ballot_sync(0xFFFFFFFFu, pi0 | pi1 | pg0 | pg1) == 0) continue;
 
-            // ---- slow path: lane t takes structure k-mer t of the block against each flagged lane's rows
+            // ---- exact path: lane t takes streamed word t of the block against the candidate lanes' row groups
             const uint32_t v = sblk[lane];
-            const int x = x0 + b * 32 + lane;
-            while (mask) {
-                const int L = __ffs(mask) - 1;
-                mask &= mask - 1;
-                #pragma unroll
-                for (int q = 0; q < K2_R; ++q) {
-                    const uint32_t rq = __shfl_sync(0xFFFFFFFFu, r[q], L);
-                    if (rq == v) {
-                        const int y = rc * K2_ROWS + L * K2_R + q;
-                        const uint8_t* cr = p.code + opr.code_off + y;
-                        bool ok = true;
-                        if (v & H_NEEDS_VERIFY)
-                            ok = verify_kmer(cr, p.code + ops_.code_off + pl.miss + x, opr.k);
-                        if (ok) {
-                            const uint32_t mult = 1u + (uint32_t)(cr[0] >> 7);
-                            const uint32_t slot = atomicAdd(&p.cnt[lo], mult);
-                            if (slot + mult <= pl.cap) {
-                                uint2* out = p.hits + pl.hit_off + slot;
-                                out[0] = make_uint2((uint32_t)x, (uint32_t)y);
-                                if (mult == 2) out[1] = make_uint2((uint32_t)x, (uint32_t)y);
-                            } else {
-                                *p.overflow = 1u;
-                            }
+            const unsigned m0 = __ballot_sync(0xFFFFFFFFu, pi0);
+            const unsigned m1 = __ballot_sync(0xFFFFFFFFu, pi1);
+            const unsigned m2 = __ballot_sync(0xFFFFFFFFu, pg0);
+            const unsigned m3 = __ballot_sync(0xFFFFFFFFu, pg1);
+            unsigned mall = m0 | m1 | m2 | m3;
+            while (mall) {
+                const int L = __ffs(mall) - 1;
+                mall &= mall - 1;
+                uint32_t hm = 0;                                     // rows of lane L equal to this lane's v
+                if ((m0 >> L) & 1u) hm |= k2_match_rows<0, NI / 2, 2>(r, L, v);
+                if ((m1 >> L) & 1u) hm |= k2_match_rows<1, NI / 2, 2>(r, L, v);
+                if (NP > 0 && ((m2 >> L) & 1u)) hm |= k2_match_rows<NI, (NP > 0 ? K2_D : 0), 1>(r, L, v);
+                if (NP > 1 && ((m3 >> L) & 1u)) hm |= k2_match_rows<(NP > 1 ? NI + K2_D : 0), (NP > 1 ? K2_D : 0), 1>(r, L, v);
+                while (hm) {                                         // ~1e-4 of the cells get here
+                    const int q = __ffs(hm) - 1;
+                    hm &= hm - 1;
+                    const int cs_ = stream0 - shift + b * 32 + lane;  // coordinate on the streamed axis
+                    const int cr_ = row0 + q * 32 + L;                // coordinate on the row axis
+                    const int x = swap ? cr_ : cs_;                   // structure k-mer
+                    const int y = swap ? cs_ : cr_;                   // read k-mer
+                    if ((v & H_NEEDS_VERIFY) &&
+                        !verify_kmer(p.code + opr.code_off + y, p.code + ops_.code_off + pl.miss + x, opr.k)) continue;
+                    const uint32_t mult = 1u + ((v >> 30) & 1u);     // H_PALINDROME: the reference appends the dot twice
+                    if (pl.kind & PLOT_QC) {                         // self-plot QC: count, store nothing
+                        uint32_t* qc = p.qc + pl.hit_off * QC_WORDS;
+                        atomicAdd(&qc[0], mult);
+                        if (x == y) atomicAdd(&qc[1], mult);
+                        else if (x > y) {
+                            atomicAdd(&qc[2], mult);
+                            atomicMin(&qc[3], (uint32_t)x); atomicMax(&qc[4], (uint32_t)x);
+                            atomicMin(&qc[5], (uint32_t)y); atomicMax(&qc[6], (uint32_t)y);
                         }
+                        continue;
+                    }
+                    const uint32_t slot = atomicAdd(&p.cnt[lo], mult);
+                    if (slot + mult <= pl.cap) {
+                        uint2* out = p.hits + pl.hit_off + slot;
+                        out[0] = make_uint2((uint32_t)x, (uint32_t)y);
+                        if (mult == 2) out[1] = make_uint2((uint32_t)x, (uint32_t)y);
+                    } else {
+                        *p.overflow = 1u;
                     }
                 }
             }

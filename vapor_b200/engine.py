@@ -219,6 +219,10 @@ class Engine:
                 raise KeyError(msg)        # the reference raises KeyError from invert_base (Simple_function.pyx:1421)
             raise N.VaporNativeError(f"{what} failed ({rc}): {msg}")
 
+    def set_option(self, name: str, value: int):
+        """Named tunables of the library (``vapor_gpu_set_option``); none changes a result."""
+        self._check(self._lib.vapor_gpu_set_option(self._h, name.encode(), int(value)), f"vapor_gpu_set_option({name})")
+
     # -- scoring ---------------------------------------------------------------------------
     def score(self, batch: PackedBatch) -> Results:
         """Blocking: host buffers in, host buffers out (``vapor_gpu_score``)."""
@@ -262,6 +266,23 @@ class Engine:
             if n.value <= cap:
                 return xy[:n.value]
             cap = int(n.value)
+
+    def selfplot_qc(self, seqs, ks) -> np.ndarray:
+        """Self-plot counts for ``window_size_refine`` (``vapor_gpu_selfplot_qc``): one row per sequence,
+        columns H, diag, lower, min x, max x, min y, max y, status."""
+        arrs = [_as_u8(s) for s in seqs]
+        n = len(arrs)
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(a) for a in arrs], out=off[1:])
+        data = np.ascontiguousarray(np.concatenate(arrs) if n and off[-1] else np.zeros(0, np.uint8), dtype=np.uint8)
+        kk = np.ascontiguousarray(np.asarray(ks, dtype=np.uint8).reshape(-1))
+        if len(kk) != n:
+            raise ValueError("one k per sequence")
+        out = np.zeros((n, 8), dtype=np.int64)
+        rc = self._lib.vapor_gpu_selfplot_qc(self._h, data.ctypes.data if len(data) else None, off.ctypes.data, n,
+                                             kk.ctypes.data if n else None, out.ctypes.data if n else None)
+        self._check(rc, "vapor_gpu_selfplot_qc")
+        return out
 
     def summarize(self, score_lists):
         """QS/GS/GT/GQ for a list of per-SV score lists (kernel 4 alone, ``vapor_gpu_summarize``).
