@@ -33,7 +33,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     """Compile the kernels + C-ABI with nvcc for sm_100a.  Returns the library path."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("VAPOR_NVCC_EXTRA", "").split()          # experiments only, e.g. -DK2_MINB=6
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

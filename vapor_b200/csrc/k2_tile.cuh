@@ -36,6 +36,7 @@ constexpr int K2_TS      = 2048;               // streamed k-mers per strip
 constexpr int K2_WARPS   = 4;                  // warps per CTA
 constexpr int K2_THREADS = 32 * K2_WARPS;
 constexpr int K2_SBUF    = K2_TS + 40;         // words per warp buffer (alignment shift + vote-block padding)
+constexpr int K2_QCAP    = 64;                 // per-warp queue of matched cells awaiting emission
 
 // tile variants: (rows by ISETP, row polynomials).  Variant 1 is the product default.
 constexpr int K2_NVARIANT = 3;
@@ -123,8 +124,72 @@ __device__ __forceinline__ uint32_t k2_match_rows(const uint32_t (&r)[R], int L,
     return hm;
 }
 
+// Matched cells are parked in a per-warp shared-memory queue by the exact path and emitted here, one cell
+// per lane: hashed words are confirmed on the code strings, the hit count of the plot is bumped once per
+// batch (a single atomic for up to 32 cells instead of one round trip per cell) and the hits are appended.
+struct K2Strip {                 // what emission needs to know about the current strip
+    const uint8_t* code_read;    // code string of the read operand
+    const uint8_t* code_struct;  // code string of the structure operand, at the cut
+    uint32_t* cnt;               // hit counter of the plot
+    uint2* hits;                 // hit list of the plot
+    uint32_t* qc;                // QC counters of the plot, or null
+    uint32_t* overflow;
+    uint32_t cap;
+    int k;
+    bool swap;                   // rows = structure k-mers, stream = read k-mers
+};
+
+__device__ __forceinline__ void k2_flush(const K2Strip& st, const uint2* queue, int qn, int lane)
+{
+    for (int base = 0; base < qn; base += 32) {
+        const int i = base + lane;
+        const bool have = i < qn;
+        const uint2 e = have ? queue[i] : make_uint2(0u, 0u);
+        const int cs_ = (int)(e.x & 0x0FFFFFFFu), cr_ = (int)e.y;
+        const int x = st.swap ? cr_ : cs_;                           // structure k-mer
+        const int y = st.swap ? cs_ : cr_;                           // read k-mer
+        bool ok = have;
+        if (have && (e.x & H_NEEDS_VERIFY)) ok = verify_kmer(st.code_read + y, st.code_struct + x, st.k);
+        const uint32_t mult = ok ? 1u + ((e.x >> 30) & 1u) : 0u;     // H_PALINDROME: the reference appends the dot twice
+        if (st.qc) {                                                 // self-plot QC: count, store nothing
+            if (mult) {
+                atomicAdd(&st.qc[0], mult);
+                if (x == y) atomicAdd(&st.qc[1], mult);
+                else if (x > y) {
+                    atomicAdd(&st.qc[2], mult);
+                    atomicMin(&st.qc[3], (uint32_t)x); atomicMax(&st.qc[4], (uint32_t)x);
+                    atomicMin(&st.qc[5], (uint32_t)y); atomicMax(&st.qc[6], (uint32_t)y);
+                }
+            }
+            continue;
+        }
+        uint32_t incl = mult;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t slot0 = 0;
+        if (lane == 31 && incl) slot0 = atomicAdd(st.cnt, incl);
+        slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 31);
+        if (mult) {
+            const uint32_t slot = slot0 + incl - mult;
+            if (slot + mult <= st.cap) {
+                st.hits[slot] = make_uint2((uint32_t)x, (uint32_t)y);
+                if (mult == 2) st.hits[slot + 1] = make_uint2((uint32_t)x, (uint32_t)y);
+            } else {
+                *st.overflow = 1u;
+            }
+        }
+    }
+}
+
+#ifndef K2_MINB
+#define K2_MINB 5                              // resident CTAs per SM the register allocation aims for
+#endif
+
 template <int NI, int NP>
-__global__ void __launch_bounds__(K2_THREADS, 5)
+__global__ void __launch_bounds__(K2_THREADS, K2_MINB)
 k2_tile_match(const K2Params p)
 {
     constexpr int R = NI + K2_D * NP;              // rows per lane; row q of lane l is strip row q*32 + l
@@ -132,11 +197,14 @@ k2_tile_match(const K2Params p)
     static_assert(NI % 2 == 0 && NP <= 2 && R <= 32, "row split");
     __shared__ __align__(16) uint32_t s_buf[K2_WARPS][K2_SBUF];
     __shared__ __align__(8) uint64_t s_bar[K2_WARPS];
+    __shared__ __align__(8) uint2 s_queue[K2_WARPS][K2_QCAP];
+    __shared__ K2Strip s_strip[K2_WARPS];           // read only by the (rare) emission code: keeps it out of registers
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     uint32_t* sb = s_buf[warp];
     uint64_t* bar = &s_bar[warp];
+    uint2* queue = s_queue[warp];
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -184,6 +252,14 @@ k2_tile_match(const K2Params p)
                 stream0 = lt * K2_TS; stream_valid = min(K2_TS, pl.m - stream0); stream_elem = struct_words + stream0;
             }
         }
+
+        K2Strip& st = s_strip[warp];
+        if (lane == 0) {
+            st.code_read = p.code + opr.code_off; st.code_struct = p.code + ops_.code_off + pl.miss;
+            st.cnt = p.cnt + lo; st.hits = p.hits + pl.hit_off; st.overflow = p.overflow; st.cap = pl.cap; st.k = opr.k; st.swap = swap;
+            st.qc = (pl.kind & PLOT_QC) ? p.qc + pl.hit_off * QC_WORDS : nullptr;
+        }
+        int qn = 0;                                                  // cells parked in the queue
 
         // ---- stage the streamed words with one TMA bulk copy ---------------------------------------
         const int shift = (int)(stream_elem & 3);                    // TMA wants a 16-byte aligned source
@@ -274,38 +350,24 @@ k2_tile_match(const K2Params p)
                 if ((m1 >> L) & 1u) hm |= k2_match_rows<1, NI / 2, 2>(r, L, v);
                 if (NP > 0 && ((m2 >> L) & 1u)) hm |= k2_match_rows<NI, (NP > 0 ? K2_D : 0), 1>(r, L, v);
                 if (NP > 1 && ((m3 >> L) & 1u)) hm |= k2_match_rows<(NP > 1 ? NI + K2_D : 0), (NP > 1 ? K2_D : 0), 1>(r, L, v);
-                while (hm) {                                         // ~1e-4 of the cells get here
-                    const int q = __ffs(hm) - 1;
-                    hm &= hm - 1;
-                    const int cs_ = stream0 - shift + b * 32 + lane;  // coordinate on the streamed axis
-                    const int cr_ = row0 + q * 32 + L;                // coordinate on the row axis
-                    const int x = swap ? cr_ : cs_;                   // structure k-mer
-                    const int y = swap ? cs_ : cr_;                   // read k-mer
-                    if ((v & H_NEEDS_VERIFY) &&
-                        !verify_kmer(p.code + opr.code_off + y, p.code + ops_.code_off + pl.miss + x, opr.k)) continue;
-                    const uint32_t mult = 1u + ((v >> 30) & 1u);     // H_PALINDROME: the reference appends the dot twice
-                    if (pl.kind & PLOT_QC) {                         // self-plot QC: count, store nothing
-                        uint32_t* qc = p.qc + pl.hit_off * QC_WORDS;
-                        atomicAdd(&qc[0], mult);
-                        if (x == y) atomicAdd(&qc[1], mult);
-                        else if (x > y) {
-                            atomicAdd(&qc[2], mult);
-                            atomicMin(&qc[3], (uint32_t)x); atomicMax(&qc[4], (uint32_t)x);
-                            atomicMin(&qc[5], (uint32_t)y); atomicMax(&qc[6], (uint32_t)y);
-                        }
-                        continue;
+                // park the matched cells (about 1e-4 of all cells) in the queue: slots by ballot + popc
+                while (true) {
+                    const unsigned act = __ballot_sync(0xFFFFFFFFu, hm != 0u);
+                    if (act == 0u) break;
+                    if (qn + __popc(act) > K2_QCAP) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
+                    if (hm) {
+                        const int q = __ffs(hm) - 1;
+                        hm &= hm - 1;
+                        const uint32_t cs_ = (uint32_t)(stream0 - shift + b * 32 + lane);   // coordinate on the streamed axis
+                        const uint32_t cr_ = (uint32_t)(row0 + q * 32 + L);                  // coordinate on the row axis
+                        queue[qn + __popc(act & ((1u << lane) - 1u))] = make_uint2(cs_ | (v & 0xC0000000u), cr_);
                     }
-                    const uint32_t slot = atomicAdd(&p.cnt[lo], mult);
-                    if (slot + mult <= pl.cap) {
-                        uint2* out = p.hits + pl.hit_off + slot;
-                        out[0] = make_uint2((uint32_t)x, (uint32_t)y);
-                        if (mult == 2) out[1] = make_uint2((uint32_t)x, (uint32_t)y);
-                    } else {
-                        *p.overflow = 1u;
-                    }
+                    qn += __popc(act);
                 }
             }
         }
+        __syncwarp();
+        if (qn) k2_flush(st, queue, qn, lane);
         __syncwarp();       // every lane is done with sb before the next strip's copy lands
     }
 }
