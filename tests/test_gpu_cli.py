@@ -1,0 +1,82 @@
+"""End-to-end on the GPU: ``vapor bed`` / ``vapor vcf`` through the real CUDA engine must reproduce the tables the
+unmodified reference CLI wrote for the committed synthetic case (tests/golden/make_cli_golden.py), and the drop-in
+single-call functions must agree with the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import vapor_oracle as O
+from vapor_b200 import Simple_function as SF
+from vapor_b200 import synth
+
+import cli_common as CC
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def session(engine):
+    s = SF.Session(engine=engine)
+    SF.set_session(s)
+    yield s
+    SF.set_session(None)
+
+
+def test_bed_cli_matches_reference_golden(tmp_path, session):
+    CC.run_bed_case(tmp_path, session)
+    assert session.stats["reads_scored"] > 50
+
+
+def test_vcf_cli_matches_reference_golden(tmp_path, session):
+    CC.run_vcf_case(tmp_path, session)
+
+
+def test_disdup_driver_matches_reference_golden(session):
+    CC.run_disdup_case(session)
+
+
+def test_dropin_single_calls(session):
+    rng = np.random.default_rng(23)
+    case = synth.make_sv_case(rng, "INV", 700, genotype=1)
+    ref, alt = case.ref_seq.tobytes().decode(), case.alt_seq.tobytes().decode()
+    reads, _ = synth.simulate_reads(rng, case.hap_alt, np.array([0]), np.array([int(case.read_window * 1.12) + 60]),
+                                    np.array([case.read_window]))
+    x = [reads.tobytes().decode(), 2, "q1"]
+    assert SF.dotdata(10, x[0], ref) == [tuple(r) for r in O.dotdata(10, x[0], ref).tolist()]
+    for name in ("calcu_vapor_single_read_score_abs_dis_m1b", "calcu_vapor_single_read_score_within_10Perc_m1b",
+                 "calcu_vapor_single_read_score_directed_dis_m1b_redefine_diagnal"):
+        got = getattr(SF, name)(ref, alt, x, 10)
+        exp = getattr(O, name)(ref, alt, x, 10)
+        assert [float(v) for v in got] == [float(v) for v in exp], name
+    assert SF.window_size_refine(ref)[0] == 10
+    assert SF.window_size_refine("ACGT")[0] == "Error"
+    assert SF.window_size_refine("N" * 150 + ref)[0] == "Error"
+    row = SF.result_organize_ins(["k", [0.5, -0.2, 0.004, 0.9]])
+    exp = O.result_organize_ins(["k", [0.5, -0.2, 0.004, 0.9]])
+    assert row[0] == exp[0] and abs(row[1] - exp[1]) < 1e-12 and row[2] == exp[2] and row[3] == exp[3]
+    gt, gq = SF.gt_estimate_log_likelihood(row)
+    egt, egq = O.gt_estimate_log_likelihood(exp)
+    assert gt == egt and abs(gq - egq) <= 1e-3
+    assert SF.result_organize_ins(["k", []]) == ["k", "NA", "NA", "NA"]
+
+
+def test_two_sessions_same_output(tmp_path, engine):
+    """Sharding the events over two sessions (here two handles on the same GPU) gives byte-identical tables."""
+    from vapor_b200 import cli
+    from vapor_b200.engine import Engine
+    outs = []
+    for n in (1, 2):
+        sessions = [SF.Session(engine=engine)] + [SF.Session(engine=Engine(0)) for _ in range(n - 1)]
+        out = os.path.join(str(tmp_path), f"bed_{n}.vapor")
+        args = CC.Args(sv_input=os.path.join(CC.CASE, "svs.bed"), output_path=os.path.join(str(tmp_path), "figs"), output_file=out,
+                       reference=os.path.join(CC.CASE, "ref.fa"), pacbio_input=os.path.join(CC.CASE, "reads.sam.gz"))
+        SF.set_session(sessions[0])
+        try:
+            cli.run_bed(args, sessions)
+        finally:
+            SF.set_session(None)
+            for s in sessions[1:]:
+                s.close()
+        outs.append(open(out).read())
+    assert outs[0] == outs[1]
