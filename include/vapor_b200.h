@@ -164,7 +164,9 @@ int vapor_gpu_host_alloc(void** p, int64_t bytes);
 int vapor_gpu_host_free(void* p);
 
 /* Integer-issue microbenchmark used as the roofline denominator of the tile kernel:
- * which = 0: 32-bit compare-accumulate (ISETP) lane-ops/s, 1: LOP3 lane-ops/s, 2: IADD3 lane-ops/s. */
+ * which = 0: 32-bit compare-accumulate (ISETP) lane-ops/s, 1: LOP3 lane-ops/s, 2: IADD3 lane-ops/s (alu pipe alone),
+ * 3: independent LOP3 + IMAD streams (alu pipe + fma pipe together: the dual-pipe integer issue rate the tile
+ * kernel's inner loop is written for). */
 int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s);
 
 /* The hit checksum mixer (host-callable; same function the kernels use). */

@@ -72,7 +72,7 @@ struct Wave {
 
 // kernel-3 scratch classes: bins that fit in shared memory, then a global-memory fallback
 constexpr int K3_NCLASS = 5;
-const int k3_class_cap[K3_NCLASS - 1] = {4096, 12288, 24576, 43000};
+const int k3_class_cap[K3_NCLASS - 1] = {4096, 16384, 49152, 180000};
 
 struct Handle {
     int device = 0;
@@ -645,6 +645,20 @@ __global__ void __launch_bounds__(256) k_int_peak(const uint32_t* __restrict__ i
         #pragma unroll
         for (int q = 0; q < 32; ++q) a ^= r[q];
         if (a == 0x12345678u) out[0] = a;
+    } else if (WHICH == 3) {
+        // both integer pipes at once: 16 independent LOP3 chains (alu pipe) + 16 independent IMAD chains (fma pipe)
+        for (int it = 0; it < iters; ++it) {
+            #pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                r[q] = (r[q] ^ v) & (r[(q + 1) & 15] | v);
+                r[16 + q] = r[16 + q] * v + r[16 + ((q + 3) & 15)];
+            }
+            v += 0x9E3779B9u;
+        }
+        uint32_t a = 0;
+        #pragma unroll
+        for (int q = 0; q < 32; ++q) a ^= r[q];
+        if (a == 0x12345678u) out[0] = a;
     } else {
         for (int it = 0; it < iters; ++it) {
             #pragma unroll
@@ -935,7 +949,7 @@ int vapor_gpu_host_free(void* p) {
 }
 
 int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s) {
-    if (!handle || !lane_ops_per_s || which < 0 || which > 2) return VAPOR_E_ARG;
+    if (!handle || !lane_ops_per_s || which < 0 || which > 3) return VAPOR_E_ARG;
     Handle* h = static_cast<Handle*>(handle);
     CK(cudaSetDevice(h->device));
     DevBuf<uint32_t> in, out;
@@ -951,6 +965,7 @@ int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s) {
         CK(cudaEventRecord(a, h->stream));
         if (which == 0) k_int_peak<0><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         else if (which == 1) k_int_peak<1><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
+        else if (which == 3) k_int_peak<3><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         else k_int_peak<2><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         CK(cudaEventRecord(b, h->stream));
         CK(cudaStreamSynchronize(h->stream));

@@ -10,10 +10,12 @@
 //   the three calcu_vapor_single_read_score_* gate ladders     :182-203, 241-257, 277-294
 //   and the per-read combine of the L2 drivers                 :1718-1726, 1913-1915
 //
-// The reference clusters by sorting; here a value histogram over y-x (resp. y+x) in shared
-// memory plays the sorted list: chain groups ("successive difference < 10") are runs of
-// occupied bins separated by >= 9 empty bins, found with bitmaps + popc, their sizes with one
-// block-wide prefix sum.  All statistics are exact integer sums; the only floating-point
+// The reference clusters by sorting; here a *bitmap* of the occupied values of y-x (resp. y+x)
+// in shared memory plays the sorted list: chain groups ("successive difference < 10") are runs
+// of set bits separated by >= 9 clear bits, found with shifts + popc; a dot's group is the rank
+// of its run (popc prefix), group sizes are counted per dot with warp-aggregated shared-memory
+// atomics.  The cost of a clustering round is O(dots + range/32), the scratch 1.2 bytes per
+// value of the range.  All statistics are exact integer sums; the only floating-point
 // operations are the final IEEE divisions the reference also performs, so results are
 // bit-identical, not merely within tolerance.
 #pragma once
@@ -23,20 +25,19 @@ namespace vb {
 
 constexpr int K3_THREADS = 256;
 
-// scratch layout in 32-bit words for a capacity of NB bins
+// scratch layout in 32-bit words for a value range of NB
 __host__ __device__ inline int k3_words_bitmap(int nb) { return (nb + 31) / 32 + 1; }
 __host__ __device__ inline int k3_words_groups(int nb) { return nb / 10 + 4; }
 __host__ __device__ inline size_t k3_scratch_words(int nb) {
-    return (size_t)nb + 3 * (size_t)k3_words_bitmap(nb) + 2 * (size_t)k3_words_groups(nb) + 8;
+    return 3 * (size_t)k3_words_bitmap(nb) + 2 * (size_t)k3_words_groups(nb) + 8;
 }
 
 struct K3Scratch {
-    uint32_t* P;        // [nb]   histogram, then inclusive prefix sum
-    uint32_t* present;  // bitmap of occupied bins
+    uint32_t* present;  // bitmap of occupied values
     uint32_t* start;    // bitmap of group starts
     uint32_t* wpref;    // [W+1] exclusive prefix of popc(start[w])
-    uint32_t* slist;    // [ng+1] start bin of every group (+ sentinel nb)
-    uint32_t* gsize;    // [ng]   hits in every group
+    uint32_t* gsize;    // [ng]   dots in every group
+    uint32_t* aux;      // [nb/10+4] small histogram (median of the modal sub-bin)
 };
 
 struct K3Shared {       // block-wide accumulators (static shared memory)
@@ -54,12 +55,11 @@ struct K3Shared {       // block-wide accumulators (static shared memory)
 
 __device__ __forceinline__ void k3_setup_scratch(K3Scratch& s, uint32_t* base, int nb_cap) {
     const int wb = k3_words_bitmap(nb_cap), wg = k3_words_groups(nb_cap);
-    s.P = base;
-    s.present = s.P + nb_cap;
+    s.present = base;
     s.start = s.present + wb;
     s.wpref = s.start + wb;
-    s.slist = s.wpref + wb;
-    s.gsize = s.slist + wg;
+    s.gsize = s.wpref + wb;
+    s.aux = s.gsize + wg;
 }
 
 // inclusive prefix sum of arr[0..N) in place; every thread of the block must call it
@@ -86,18 +86,37 @@ __device__ void k3_block_scan(uint32_t* arr, int N, K3Shared& sh) {
     __syncthreads();
 }
 
-// From the histogram in s.P[0..nb) build the chain groups (runs of occupied bins whose gaps are
-// < 10) and their sizes.  On return s.P holds the inclusive prefix sum, sh.ng the group count,
-// sh.gmax the largest group.  Every thread of the block must call it.
-__device__ void k3_build_groups(K3Scratch& s, int nb, K3Shared& sh) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Counter increment for a whole warp at once.  The dots of a read pile up in one or two groups, so a plain
+// shared-memory atomic per dot serialises 32 ways; lanes with the same index elect one lane to add their
+// count.  Call from converged code; `idx < 0` = this lane has nothing to add.
+__device__ __forceinline__ void k3_warp_count_add(uint32_t* C, int idx) {
+    const int lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, idx < 0 ? -1 - lane : idx);
+    if (idx >= 0 && lane == __ffs(peers) - 1) atomicAdd(&C[idx], (uint32_t)__popc(peers));
+}
+
+__device__ __forceinline__ int k3_group_of(const K3Scratch& s, int b) {
+    const int w = b >> 5;
+    return (int)s.wpref[w] + __popc(s.start[w] & (0xFFFFFFFFu >> (31 - (b & 31)))) - 1;
+}
+
+// Chain groups of the values binf(hit) in [0, nb) over the hits of a plot (binf < 0 = hit not taken): runs of
+// occupied values whose gaps are < 10, and their sizes.  On return k3_group_size() answers per value, sh.ng is
+// the group count, sh.gmax the largest group.  Every thread of the block must call it.
+template <typename BinF>
+__device__ void k3_build_groups(const uint2* hits, uint32_t H, K3Scratch& s, int nb, K3Shared& sh, BinF binf) {
+    const int tid = threadIdx.x, lane = tid & 31;
     const int W = (nb + 31) >> 5;
-    for (int w = warp; w < W; w += K3_THREADS / 32) {
-        const int b = w * 32 + lane;
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, b < nb && s.P[b] != 0);
-        if (lane == 0) s.present[w] = bal;
-    }
+    for (int w = tid; w < W; w += K3_THREADS) s.present[w] = 0u;
     if (tid == 0) { sh.gmax = 0; s.wpref[0] = 0; }
+    __syncthreads();
+    for (uint32_t i = tid; i < H; i += K3_THREADS) {
+        const int b = binf(hits[i]);
+        if (b >= 0) {
+            const uint32_t bit = 1u << (b & 31);
+            if (!(s.present[b >> 5] & bit)) atomicOr(&s.present[b >> 5], bit);      // most dots re-set a bit already set
+        }
+    }
     __syncthreads();
     for (int w = tid; w < W; w += K3_THREADS) {
         const uint32_t cur = s.present[w], prev = w ? s.present[w - 1] : 0u;
@@ -110,27 +129,20 @@ __device__ void k3_build_groups(K3Scratch& s, int nb, K3Shared& sh) {
         s.wpref[w + 1] = __popc(st);
     }
     __syncthreads();
-    k3_block_scan(s.P, nb, sh);
     k3_block_scan(s.wpref + 1, W, sh);
     const int ng = (int)s.wpref[W];
-    for (int w = tid; w < W; w += K3_THREADS) {
-        uint32_t bits = s.start[w];
-        int idx = (int)s.wpref[w];
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            s.slist[idx++] = (uint32_t)(w * 32 + b);
-        }
+    for (int g = tid; g < ng; g += K3_THREADS) s.gsize[g] = 0u;
+    if (tid == 0) sh.ng = ng;
+    __syncthreads();
+    for (uint32_t base = 0; base < H; base += K3_THREADS) {            // uniform trip count: warp-aggregated adds
+        const uint32_t i = base + tid;
+        int g = -1;
+        if (i < H) { const int b = binf(hits[i]); if (b >= 0) g = k3_group_of(s, b); }
+        k3_warp_count_add(s.gsize, g);
     }
-    if (tid == 0) { s.slist[ng] = (uint32_t)nb; sh.ng = ng; }
     __syncthreads();
     uint32_t lmax = 0;
-    for (int g = tid; g < ng; g += K3_THREADS) {
-        const uint32_t s0 = s.slist[g], s1 = s.slist[g + 1];
-        const uint32_t sz = s.P[s1 - 1] - (s0 ? s.P[s0 - 1] : 0u);
-        s.gsize[g] = sz;
-        lmax = max(lmax, sz);
-    }
+    for (int g = tid; g < ng; g += K3_THREADS) lmax = max(lmax, s.gsize[g]);
     #pragma unroll
     for (int o = 16; o; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xFFFFFFFFu, lmax, o));
     if (lane == 0 && lmax) atomicMax(&sh.gmax, lmax);
@@ -138,9 +150,7 @@ __device__ void k3_build_groups(K3Scratch& s, int nb, K3Shared& sh) {
 }
 
 __device__ __forceinline__ uint32_t k3_group_size(const K3Scratch& s, int b) {
-    const int w = b >> 5;
-    const int g = (int)s.wpref[w] + __popc(s.start[w] & (0xFFFFFFFFu >> (31 - (b & 31)))) - 1;
-    return s.gsize[g];
+    return s.gsize[k3_group_of(s, b)];
 }
 
 __device__ __forceinline__ void k3_zero(uint32_t* a, int n) {
@@ -191,30 +201,17 @@ __device__ void k3_pass0(const PlotView& v, K3Shared& sh, int& minx, int& maxx, 
 // sum |x-y| of the kept dots.
 __device__ void k3_clean_a6(const PlotView& v, K3Scratch& s, K3Shared& sh, PlotStat& st) {
     const int nb = v.n + v.m - 1;
-    k3_zero(s.P, nb);
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
-        const uint2 h = v.hits[i];
-        atomicAdd(&s.P[(int)(h.y & HIT_Y_MASK) - (int)h.x + v.m - 1], 1u);
-    }
-    __syncthreads();
-    k3_build_groups(s, nb, sh);
+    const int moff = v.m - 1;
+    k3_build_groups(v.hits, v.H, s, nb, sh, [moff](const uint2& h) { return (int)(h.y & HIT_Y_MASK) - (int)h.x + moff; });
     for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
         uint2 h = v.hits[i];
         const uint32_t y = h.y & HIT_Y_MASK;
         const bool keep = k3_group_size(s, (int)y - (int)h.x + v.m - 1) > 10u;
         v.hits[i].y = y | (keep ? HIT_F_KEEP1 : 0u);
     }
-    __syncthreads();
-    k3_zero(s.P, nb);
     if (threadIdx.x == 0) { sh.u32a = 0; sh.u64a = 0; }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
-        const uint2 h = v.hits[i];
-        atomicAdd(&s.P[(int)(h.y & HIT_Y_MASK) + (int)h.x], 1u);
-    }
-    __syncthreads();
-    k3_build_groups(s, nb, sh);
+    k3_build_groups(v.hits, v.H, s, nb, sh, [](const uint2& h) { return (int)(h.y & HIT_Y_MASK) + (int)h.x; });
     uint32_t lcnt = 0; unsigned long long lsum = 0;
     for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
         uint2 h = v.hits[i];
@@ -246,15 +243,9 @@ __device__ void k3_clean_w10(const PlotView& v, K3Scratch& s, K3Shared& sh, Plot
     st.nclean = 0; st.cnt10 = 0;
     if (v.H == 0) return;                               // uniform across the block
     const int nb = v.n + v.m - 1;
-    k3_zero(s.P, nb);
     if (threadIdx.x == 0) { sh.u32a = 0; sh.u32b = 0; sh.u32c = 0; }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
-        const uint2 h = v.hits[i];
-        atomicAdd(&s.P[(int)(h.y & HIT_Y_MASK) - (int)h.x + v.m - 1], 1u);
-    }
-    __syncthreads();
-    k3_build_groups(s, nb, sh);
+    const int moff = v.m - 1;
+    k3_build_groups(v.hits, v.H, s, nb, sh, [moff](const uint2& h) { return (int)(h.y & HIT_Y_MASK) - (int)h.x + moff; });
     const uint32_t gmax1 = sh.gmax;
     uint32_t lkept = 0;
     for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
@@ -272,14 +263,8 @@ __device__ void k3_clean_w10(const PlotView& v, K3Scratch& s, K3Shared& sh, Plot
     const bool have_left = kept1 < v.H;
     uint32_t gmax2 = 0;
     if (have_left) {
-        k3_zero(s.P, nb);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
-            const uint2 h = v.hits[i];
-            if (!(h.y & HIT_F_KEEP1)) atomicAdd(&s.P[(int)(h.y & HIT_Y_MASK) + (int)h.x], 1u);
-        }
-        __syncthreads();
-        k3_build_groups(s, nb, sh);
+        k3_build_groups(v.hits, v.H, s, nb, sh,
+                        [](const uint2& h) { return (h.y & HIT_F_KEEP1) ? -1 : (int)(h.y & HIT_Y_MASK) + (int)h.x; });
         gmax2 = sh.gmax;
     }
     uint32_t lcnt = 0, l10 = 0;
@@ -392,13 +377,13 @@ __device__ void k3_redef_stat(const PlotView& v, K3Scratch& s, K3Shared& sh, Plo
         const int b2 = sh.sel;
         if (b2 >= 0) {                                 // uniform: np.median of that sub-bin
             const uint32_t c = sh.cnt11[b2];
-            k3_zero(s.P, rg2 + 1);
+            k3_zero(s.aux, rg2 + 1);
             __syncthreads();
             for (uint32_t i = tid; i < v.H; i += K3_THREADS) {
                 const uint2 h = v.hits[i];
                 if (h.y & HIT_F_CLEAN) {
                     const int d = (int)(h.y & HIT_Y_MASK) - (int)h.x;
-                    if (k3_bin11(d, mn1, rg1) == b1 && k3_bin11(d, mn2, rg2) == b2) atomicAdd(&s.P[d - mn2], 1u);
+                    if (k3_bin11(d, mn1, rg1) == b1 && k3_bin11(d, mn2, rg2) == b2) atomicAdd(&s.aux[d - mn2], 1u);
                 }
             }
             __syncthreads();
@@ -406,7 +391,7 @@ __device__ void k3_redef_stat(const PlotView& v, K3Scratch& s, K3Shared& sh, Plo
                 const uint32_t r0 = (c - 1) / 2, r1 = c / 2;
                 uint32_t cum = 0; int v0 = -1, v1 = -1;
                 for (int t = 0; t <= rg2 && v1 < 0; ++t) {
-                    cum += s.P[t];
+                    cum += s.aux[t];
                     if (v0 < 0 && cum > r0) v0 = t;
                     if (cum > r1) v1 = t;
                 }
