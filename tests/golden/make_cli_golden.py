@@ -57,8 +57,8 @@ def main():
     from vapor_b200 import synth_genome
     if os.path.isdir(CASE):
         shutil.rmtree(CASE)
-    ds = synth_genome.make_dataset(CASE, seed=20261018, n_simple=8, n_complex=4, size_range=(60, 900), coverage=16.0,
-                                   read_len_mean=6000.0, complex_types=("DEL_INV", "DUP_INV", "OTHER", "DISDUP"))
+    ds = synth_genome.make_dataset(CASE, seed=20261018, n_simple=8, n_complex=5, size_range=(60, 900), coverage=16.0,
+                                   read_len_mean=6000.0, complex_types=("DEL_INV", "DUP_INV", "OTHER", "DISDUP", "OTHER2"))
     with open(ds.sam, "rb") as f, gzip.GzipFile(ds.sam + ".gz", "wb", mtime=0) as g:
         shutil.copyfileobj(f, g)
     os.remove(ds.sam)

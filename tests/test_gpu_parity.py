@@ -174,3 +174,61 @@ def test_selfplot_qc_counts(engine):
         assert got[i, 7] == 1
     bad = base[:400].copy(); bad[77] = ord("X")
     assert engine.selfplot_qc([bad], [10])[0, 7] == 2
+
+
+@pytest.mark.parametrize("svtype,svlen,k,mode", [
+    ("INV", 12000, 10, MODE_ABS), ("TANDUP", 30000, 20, MODE_REDEF), ("DEL", 60000, 30, MODE_W10),
+    ("INV", 100000, 40, MODE_ABS), ("INS", 20000, 10, MODE_W10), ("TANDUP", 11000, 10, MODE_ABS_AND_W10)])
+def test_large_windows(engine, svtype, svlen, k, mode):
+    """BASELINE config 4: 10-100 kb windows.  The reference drivers never plot that much (they fall back to 1 kb
+    junction windows at >= 10 kb, Simple_function.pyx:1728), but its scoring functions accept any length; these
+    plots span many strips on both axes, transposed tails, several kernel-3 scratch classes and every k."""
+    rng = np.random.default_rng(svlen + k)
+    case = synth.make_sv_case(rng, svtype, svlen, genotype=1)
+    b = Batch()
+    rid, aid = b.add_seq(case.ref_seq), b.add_seq(case.alt_seq)
+    for hap, miss in ((case.hap_alt, 0), (case.hap_ref, 3)):
+        want = case.read_window - miss
+        reads, _ = synth.simulate_reads(rng, hap, np.array([miss]), np.array([min(len(hap) - miss, int(want * 1.12) + 60)]),
+                                        np.array([want]))
+        b.add_task(b.add_seq(reads), rid, aid, miss, k, mode)
+    b.end_sv(svtype)
+    pb = b.pack()
+    res = engine.score(pb)
+    _compare(res, BO.score_batch(pb))
+
+
+def test_properties_at_benchmark_scale(engine):
+    """Size-independent properties on a batch too large for the oracle to score in full (BASELINE config 2 sizes):
+    (1) waves: a 64 MB hit budget (many waves) gives byte-identical results to one wave; (2) sharding: scoring the
+    SVs in two halves and merging equals scoring them together; (3) the tile variants (ISETP-only vs dual-pipe
+    inner loop) give identical hit counts and coordinate checksums; (4) a sample of SVs agrees with the oracle."""
+    from vapor_b200 import multi
+    from vapor_b200.engine import Engine
+    w = synth.make_workload(120, seed=77, size_range=(50, 5000), reads_per_sv=20)
+    base = engine.score(w.batch)
+    assert (base.task_status == 1).sum() > 0.5 * w.batch.n_task
+    small = Engine(0, hit_budget_bytes=64 << 20)
+    try:
+        waves = small.score(w.batch)
+        assert small.timings()["n_waves"] > 1
+        small.set_option("tile_variant", 0)
+        v0 = small.score(w.batch)
+    finally:
+        small.close()
+    for f in base.__dataclass_fields__:
+        np.testing.assert_array_equal(getattr(waves, f), getattr(base, f), err_msg=f)
+        np.testing.assert_array_equal(getattr(v0, f), getattr(base, f), err_msg=f)
+    import threading
+    lock = threading.Lock()                                  # one handle is not re-entrant: serialise the two shards
+
+    def one_at_a_time(pb):
+        with lock:
+            return engine.score(pb)
+    merged = multi.score_sharded(w.batch, [one_at_a_time, one_at_a_time])
+    for f in base.__dataclass_fields__:
+        np.testing.assert_array_equal(getattr(merged, f), getattr(base, f), err_msg=f)
+    sample = w.batch.shard([3, 17, 58, 111])
+    exp = BO.score_batch(sample)
+    got = engine.score(sample)
+    _compare(got, exp)

@@ -203,18 +203,25 @@ def make_dataset(out_dir: str, seed: int = 20261018, n_simple: int = 8, n_comple
             seg = [("del", s, m_), ("ref", m_, e), ("ins", ref[s:m_].copy())]
             sv = PlantedSV(svid, kind, chrom, s, e, gt, extra={"bps": [s, m_, e], "ref": "ab", "alt": "ba"})
             span_end = e
+        elif kind == "OTHER2":                                     # two different alternative alleles: a (b deleted) and ba
+            m_ = s + L
+            e = m_ + max(80, L // 2)
+            seg = [("del", s, m_), ("ref", m_, e), ("ins", ref[s:m_].copy())]          # haplotype B: ba
+            seg_a = [("ref", s, m_), ("del", m_, e)]                                     # haplotype A: a
+            sv = PlantedSV(svid, kind, chrom, s, e, 2, extra={"bps": [s, m_, e], "ref": "ab", "alt": "a/ba"})
+            span_end = e
         else:
             raise ValueError(kind)
         svs.append(sv)
-        per_sv_segments.append((s, span_end, seg))
+        per_sv_segments.append((s, span_end, seg, seg_a if kind == "OTHER2" else None))
     # haplotypes: A carries hom-alt events only, B carries every event
     def build(which):
         segs, cur = [], 0
-        for sv, (s, span_end, seg) in zip(svs, per_sv_segments):
+        for sv, (s, span_end, seg, seg_a) in zip(svs, per_sv_segments):
             carry = sv.genotype == 2 or which == "B"
             segs.append(("ref", cur, s))
             if carry:
-                segs += seg
+                segs += seg_a if (seg_a is not None and which == "A") else seg
                 cur = span_end
             else:
                 cur = s
@@ -290,6 +297,9 @@ def make_dataset(out_dir: str, seed: int = 20261018, n_simple: int = 8, n_comple
             elif sv.svtype == "DISDUP":
                 p = sv.extra["insert_point"]
                 info = f"SVTYPE=disdup;END={sv.end};insert_point={c}:{p};Other=ab/ab_ab/aba_{c}:{sv.start}:{sv.end}:{p}"
+            elif sv.svtype == "OTHER2":
+                b0, b1, b2 = sv.extra["bps"]
+                info = f"SVTYPE=cannot_classify_for_now;END={sv.end};Other=ab/ab_a/ba_{c}:{b0}:{b1}:{b2}"
             else:
                 b0, b1, b2 = sv.extra["bps"]
                 info = f"SVTYPE=cannot_classify_for_now;END={sv.end};Other=ab/ab_ab/ba_{c}:{b0}:{b1}:{b2}"
