@@ -211,7 +211,16 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
             const uint8_t* p = in->seq_bytes + in->seq_off[s];
             const int64_t L = in->seq_off[s + 1] - in->seq_off[s];
             int8_t f = 0;
-            for (int64_t i = 0; i < L; ++i) if (p[i] >= 'a' && p[i] <= 'z') { f = 1; break; }
+            int64_t i = 0;
+            // ASCII lower-case letters have bit 5 set, upper-case ones do not: skip 8 bytes at a time while no byte has it
+            for (; i + 8 <= L; i += 8) {
+                uint64_t w8; memcpy(&w8, p + i, 8);
+                if (w8 & 0x2020202020202020ull) {
+                    for (int j = 0; j < 8; ++j) if (p[i + j] >= 'a' && p[i + j] <= 'z') { f = 1; break; }
+                    if (f) break;
+                }
+            }
+            for (; !f && i < L; ++i) if (p[i] >= 'a' && p[i] <= 'z') f = 1;
             has_lower[s] = f;
         }
         return has_lower[s] != 0;
@@ -357,11 +366,21 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
 
 int upload_impl(Handle* h, const vapor_batch_t* in) {
     h->resident = false; h->ran = false;
+    CK(cudaSetDevice(h->device));
+    // The sequence bytes are the bulk of the upload and need no planning: start that copy first, so it runs
+    // (from pinned host memory) underneath the host-side planning below.
+    int sp = -1;
+    if (in && in->seq_off && in->n_seq > 0 && in->seq_bytes && in->seq_off[0] == 0 && in->seq_off[in->n_seq] > 0 &&
+        in->seq_off[in->n_seq] < ((int64_t)1 << 40)) {
+        const size_t total = (size_t)in->seq_off[in->n_seq];
+        CK(h->d_seq.ensure(total + 64));
+        sp = span_begin(h, CAT_H2D);
+        CK(cudaMemcpyAsync(h->d_seq.p, in->seq_bytes, total, cudaMemcpyHostToDevice, h->stream));
+    }
     auto t0 = std::chrono::steady_clock::now();
     int rc = plan_batch(h, in);
-    if (rc) return rc;
+    if (rc) { if (sp >= 0) { span_end(h, sp); cudaStreamSynchronize(h->stream); h->spans.clear(); h->ev_used = 0; } return rc; }
     h->tm.host_prep_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    CK(cudaSetDevice(h->device));
     const size_t nt = (size_t)h->n_task, nsv = (size_t)h->n_sv;
     CK(h->d_seq.ensure((size_t)h->seq_total + 64));
     CK(h->d_ops.ensure(h->ops.size() + 1));
@@ -385,8 +404,10 @@ int upload_impl(Handle* h, const vapor_batch_t* in) {
     if (k3_class_of(h->max_nb) == K3_NCLASS - 1)
         CK(h->d_gscratch.ensure((size_t)2 * h->sm_count * k3_scratch_words(h->max_nb)));
 
-    int sp = span_begin(h, CAT_H2D);
-    if (h->seq_total > 0) CK(cudaMemcpyAsync(h->d_seq.p, in->seq_bytes, (size_t)h->seq_total, cudaMemcpyHostToDevice, h->stream));
+    if (sp < 0) {
+        sp = span_begin(h, CAT_H2D);
+        if (h->seq_total > 0) CK(cudaMemcpyAsync(h->d_seq.p, in->seq_bytes, (size_t)h->seq_total, cudaMemcpyHostToDevice, h->stream));
+    }
     CK(cudaMemcpyAsync(h->d_ops.p, h->ops.data(), h->ops.size() * sizeof(Operand), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_plots.p, h->plots.data(), h->plots.size() * sizeof(Plot), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_tasks.p, h->tasks.data(), nt * sizeof(Task), cudaMemcpyHostToDevice, h->stream));
