@@ -23,9 +23,13 @@
 // for each structure word v by Horner's rule (8 fma-pipe ops) and tested against zero once.
 // P(v) == 0 whenever v equals one of the 8 rows (no false negatives); a zero without a match needs
 // the factors' trailing zero bits to sum to >= 32 (about 3.5e-5 per evaluation on mixed words) and
-// only costs a visit to the exact path.  A warp vote every 32 structure k-mers sends the blocks
-// that hold a candidate to a warp-cooperative exact path that locates, confirms (hash words with
-// bit 31 set are checked on the code strings) and appends the hits.
+// only costs a visit to the exact path.  A warp vote every 32 streamed k-mers asks whether any
+// lane saw a candidate; a lane that did leaves a 4-byte note (block, lane, row group) in a
+// per-warp shared-memory list and the inner loop moves on.  The notes are resolved later, one
+// note per lane: 8 rows of the noted lane (fetched by shuffle) against the 32 words of the noted
+// block -- no dependent chain per dot, no divergence, 16 warp instructions per note.  Matched
+// cells are confirmed (hash words with bit 31 set are checked on the code strings) and appended
+// in batches of 32 with one atomic.
 #pragma once
 #include "common.cuh"
 
@@ -37,6 +41,7 @@ constexpr int K2_WARPS   = 4;                  // warps per CTA
 constexpr int K2_THREADS = 32 * K2_WARPS;
 constexpr int K2_SBUF    = K2_TS + 40;         // words per warp buffer (alignment shift + vote-block padding)
 constexpr int K2_QCAP    = 64;                 // per-warp queue of matched cells awaiting emission
+constexpr int K2_NCAP    = 192;                // per-warp list of candidate notes awaiting resolution
 
 // tile variants: (rows by ISETP, row polynomials).  Variant 1 is the product default.
 constexpr int K2_NVARIANT = 3;
@@ -109,20 +114,13 @@ struct K2Params {
     uint32_t* qc;               // [n_qc_plots * QC_WORDS] counters of PLOT_QC plots (may be null when there is none)
 };
 
-// Exact path, step 1: for candidate lane L and its rows Q0, Q0+STEP, ... (NQ of them), lane t of the warp
-// (holding streamed word v) marks the rows of L whose word equals v.  Rows are fetched by shuffle.
-template <int Q0, int NQ, int STEP, int R>
-__device__ __forceinline__ uint32_t k2_match_rows(const uint32_t (&r)[R], int L, uint32_t v)
-{
-    uint32_t hm = 0;
-    #pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-        const int q = Q0 + i * STEP;
-        const uint32_t rq = __shfl_sync(0xFFFFFFFFu, r[q], L);
-        if (rq == v) hm |= 1u << q;
-    }
-    return hm;
-}
+// Row groups of a lane: a candidate flag covers one group.  Groups 0 and 1 are the two halves of the ISETP rows,
+// groups 2 and 3 the rows of the two polynomials.
+template <int NI, int NP> struct K2Groups {
+    static constexpr int NG = 2 + NP;
+    __host__ __device__ static constexpr int base(int g) { return g == 0 ? 0 : (g == 1 ? NI / 2 : NI + K2_D * (g - 2)); }
+    __host__ __device__ static constexpr int count(int g) { return g == 0 ? NI / 2 : (g == 1 ? NI - NI / 2 : K2_D); }
+};
 
 // Matched cells are parked in a per-warp shared-memory queue by the exact path and emitted here, one cell
 // per lane: hashed words are confirmed on the code strings, the hit count of the plot is bumped once per
@@ -184,8 +182,57 @@ __device__ __forceinline__ void k2_flush(const K2Strip& st, const uint2* queue, 
     }
 }
 
+// Resolve candidate notes, one note per lane and round: the 8 rows of the noted lane's group (fetched by shuffle:
+// every lane names its own source lane) against the 32 streamed words of the noted block.  Lanes walk the block in
+// rotated order so the shared-memory reads of a round never share a bank.  Matches are parked in the hit queue.
+template <int NI, int NP, int R>
+__device__ __forceinline__ void k2_resolve(const uint32_t (&r)[R], const uint32_t* notes, int nn, const uint32_t* sb,
+                                           int stream_origin, int row0, const K2Strip& st, uint2* queue, int& qn, int lane)
+{
+    using G = K2Groups<NI, NP>;
+    for (int base = 0; base < nn; base += 32) {
+        const bool have = base + lane < nn;
+        const uint32_t note = have ? notes[base + lane] : (uint32_t)(lane << 3);
+        const int b = (int)(note >> 8), L = (int)(note >> 3) & 31, g = (int)(note & 7u);
+        uint32_t rows[K2_D];
+        #pragma unroll
+        for (int j = 0; j < K2_D; ++j) rows[j] = H_ROW_PAD;
+        #pragma unroll
+        for (int gg = 0; gg < G::NG; ++gg) {
+            #pragma unroll
+            for (int j = 0; j < G::count(gg); ++j) {
+                const uint32_t w = __shfl_sync(0xFFFFFFFFu, r[G::base(gg) + j], L);
+                if (have && g == gg) rows[j] = w;
+            }
+        }
+        const int gbase = g == 0 ? G::base(0) : (g == 1 ? G::base(1) : (g == 2 ? G::base(2) : G::base(3)));
+        const uint32_t* sblk = sb + b * 32;
+        for (int t = 0; t < 32; ++t) {
+            const int tt = (t + lane) & 31;
+            const uint32_t v = sblk[tt];
+            uint32_t hm = 0;
+            #pragma unroll
+            for (int j = 0; j < K2_D; ++j) if (rows[j] == v) hm |= 1u << j;
+            // park the matched cells (about 1e-4 of all cells): slots by ballot + popc
+            while (true) {
+                const unsigned act = __ballot_sync(0xFFFFFFFFu, hm != 0u);
+                if (act == 0u) break;
+                if (qn + __popc(act) > K2_QCAP) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
+                if (hm) {
+                    const int j = __ffs(hm) - 1;
+                    hm &= hm - 1;
+                    const uint32_t cs_ = (uint32_t)(stream_origin + b * 32 + tt);            // coordinate on the streamed axis
+                    const uint32_t cr_ = (uint32_t)(row0 + (gbase + j) * 32 + L);             // coordinate on the row axis
+                    queue[qn + __popc(act & ((1u << lane) - 1u))] = make_uint2(cs_ | (v & 0xC0000000u), cr_);
+                }
+                qn += __popc(act);
+            }
+        }
+    }
+}
+
 #ifndef K2_MINB
-#define K2_MINB 5                              // resident CTAs per SM the register allocation aims for
+#define K2_MINB 4                              // resident CTAs per SM the register allocation aims for
 #endif
 
 template <int NI, int NP>
@@ -198,6 +245,7 @@ k2_tile_match(const K2Params p)
     __shared__ __align__(16) uint32_t s_buf[K2_WARPS][K2_SBUF];
     __shared__ __align__(8) uint64_t s_bar[K2_WARPS];
     __shared__ __align__(8) uint2 s_queue[K2_WARPS][K2_QCAP];
+    __shared__ uint32_t s_notes[K2_WARPS][K2_NCAP];
     __shared__ K2Strip s_strip[K2_WARPS];           // read only by the (rare) emission code: keeps it out of registers
 
     const int warp = threadIdx.x >> 5;
@@ -205,6 +253,7 @@ k2_tile_match(const K2Params p)
     uint32_t* sb = s_buf[warp];
     uint64_t* bar = &s_bar[warp];
     uint2* queue = s_queue[warp];
+    uint32_t* notes = s_notes[warp];
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -260,6 +309,7 @@ k2_tile_match(const K2Params p)
             st.qc = (pl.kind & PLOT_QC) ? p.qc + pl.hit_off * QC_WORDS : nullptr;
         }
         int qn = 0;                                                  // cells parked in the queue
+        int nn = 0;                                                  // candidate notes awaiting resolution
 
         // ---- stage the streamed words with one TMA bulk copy ---------------------------------------
         const int shift = (int)(stream_elem & 3);                    // TMA wants a 16-byte aligned source
@@ -328,44 +378,33 @@ k2_tile_match(const K2Params p)
                         #pragma unroll
                         for (int g = 0; g < NP; ++g) acc[g] = acc[g] * v + c[g][i];
                     #pragma unroll
-                    for (int q = 0; q < NI; q += 2) { pi0 |= (r[q] == v); pi1 |= (r[q + 1] == v); }
+                    for (int q = 0; q < NI / 2; ++q) { pi0 |= (r[q] == v); pi1 |= (r[NI / 2 + q] == v); }
                     if (NP > 0) pg0 |= (acc[0] == 0u);
                     if (NP > 1) pg1 |= (acc[NP > 1 ? 1 : 0] == 0u);
                 }
             }
-            if (__ballot_sync(0xFFFFFFFFu, pi0 | pi1 | pg0 | pg1) == 0) continue;
-
-            // ---- exact path: lane t takes streamed word t of the block against the candidate lanes' row groups
-            const uint32_t v = sblk[lane];
-            const unsigned m0 = __ballot_sync(0xFFFFFFFFu, pi0);
-            const unsigned m1 = __ballot_sync(0xFFFFFFFFu, pi1);
-            const unsigned m2 = __ballot_sync(0xFFFFFFFFu, pg0);
-            const unsigned m3 = __ballot_sync(0xFFFFFFFFu, pg1);
-            unsigned mall = m0 | m1 | m2 | m3;
-            while (mall) {
-                const int L = __ffs(mall) - 1;
-                mall &= mall - 1;
-                uint32_t hm = 0;                                     // rows of lane L equal to this lane's v
-                if ((m0 >> L) & 1u) hm |= k2_match_rows<0, NI / 2, 2>(r, L, v);
-                if ((m1 >> L) & 1u) hm |= k2_match_rows<1, NI / 2, 2>(r, L, v);
-                if (NP > 0 && ((m2 >> L) & 1u)) hm |= k2_match_rows<NI, (NP > 0 ? K2_D : 0), 1>(r, L, v);
-                if (NP > 1 && ((m3 >> L) & 1u)) hm |= k2_match_rows<(NP > 1 ? NI + K2_D : 0), (NP > 1 ? K2_D : 0), 1>(r, L, v);
-                // park the matched cells (about 1e-4 of all cells) in the queue: slots by ballot + popc
-                while (true) {
-                    const unsigned act = __ballot_sync(0xFFFFFFFFu, hm != 0u);
-                    if (act == 0u) break;
-                    if (qn + __popc(act) > K2_QCAP) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
-                    if (hm) {
-                        const int q = __ffs(hm) - 1;
-                        hm &= hm - 1;
-                        const uint32_t cs_ = (uint32_t)(stream0 - shift + b * 32 + lane);   // coordinate on the streamed axis
-                        const uint32_t cr_ = (uint32_t)(row0 + q * 32 + L);                  // coordinate on the row axis
-                        queue[qn + __popc(act & ((1u << lane) - 1u))] = make_uint2(cs_ | (v & 0xC0000000u), cr_);
-                    }
-                    qn += __popc(act);
+            // ---- candidates: a lane with a flagged row group leaves a note (block, lane, group) and moves on ----
+            unsigned act = __ballot_sync(0xFFFFFFFFu, pi0 | pi1 | pg0 | pg1);
+            if (act == 0u) continue;
+            unsigned flags = (pi0 ? 1u : 0u) | (pi1 ? 2u : 0u) | (pg0 ? 4u : 0u) | (pg1 ? 8u : 0u);
+            while (act) {                                            // one pass per flagged group of the busiest lane (almost always 1)
+                if (nn + __popc(act) > K2_NCAP) {
+                    __syncwarp();
+                    k2_resolve<NI, NP>(r, notes, nn, sb, stream0 - shift, row0, st, queue, qn, lane);
+                    nn = 0;
+                    __syncwarp();
                 }
+                if (flags) {
+                    const int g = __ffs(flags) - 1;
+                    flags &= flags - 1;
+                    notes[nn + __popc(act & ((1u << lane) - 1u))] = (uint32_t)((b << 8) | (lane << 3) | g);
+                }
+                nn += __popc(act);
+                act = __ballot_sync(0xFFFFFFFFu, flags != 0u);
             }
         }
+        __syncwarp();
+        if (nn) { k2_resolve<NI, NP>(r, notes, nn, sb, stream0 - shift, row0, st, queue, qn, lane); nn = 0; }
         __syncwarp();
         if (qn) k2_flush(st, queue, qn, lane);
         __syncwarp();       // every lane is done with sb before the next strip's copy lands
