@@ -207,25 +207,38 @@ __device__ __forceinline__ void k2_resolve(const uint32_t (&r)[R], const uint32_
         }
         const int gbase = g == 0 ? G::base(0) : (g == 1 ? G::base(1) : (g == 2 ? G::base(2) : G::base(3)));
         const uint32_t* sblk = sb + b * 32;
-        for (int t = 0; t < 32; ++t) {
-            const int tt = (t + lane) & 31;
-            const uint32_t v = sblk[tt];
-            uint32_t hm = 0;
+        #pragma unroll 1
+        for (int t0 = 0; t0 < 32; t0 += 8) {                        // 8 streamed words per step: loads and compares overlap
+            uint32_t v[8];
             #pragma unroll
-            for (int j = 0; j < K2_D; ++j) if (rows[j] == v) hm |= 1u << j;
-            // park the matched cells (about 1e-4 of all cells): slots by ballot + popc
-            while (true) {
-                const unsigned act = __ballot_sync(0xFFFFFFFFu, hm != 0u);
-                if (act == 0u) break;
-                if (qn + __popc(act) > K2_QCAP) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
-                if (hm) {
-                    const int j = __ffs(hm) - 1;
-                    hm &= hm - 1;
-                    const uint32_t cs_ = (uint32_t)(stream_origin + b * 32 + tt);            // coordinate on the streamed axis
-                    const uint32_t cr_ = (uint32_t)(row0 + (gbase + j) * 32 + L);             // coordinate on the row axis
-                    queue[qn + __popc(act & ((1u << lane) - 1u))] = make_uint2(cs_ | (v & 0xC0000000u), cr_);
+            for (int e = 0; e < 8; ++e) v[e] = sblk[(t0 + e + lane) & 31];
+            bool any = false;
+            #pragma unroll
+            for (int e = 0; e < 8; ++e)
+                #pragma unroll
+                for (int j = 0; j < K2_D; ++j) any |= (rows[j] == v[e]);
+            if (__ballot_sync(0xFFFFFFFFu, any) == 0u) continue;
+            #pragma unroll 1
+            for (int e = 0; e < 8; ++e) {                           // a match somewhere in these 8 x 8 x 32 cells: find it
+                const int tt = (t0 + e + lane) & 31;
+                const uint32_t ve = sblk[tt];
+                uint32_t hm = 0;
+                #pragma unroll
+                for (int j = 0; j < K2_D; ++j) if (rows[j] == ve) hm |= 1u << j;
+                // park the matched cells (about 1e-4 of all cells): slots by ballot + popc
+                while (true) {
+                    const unsigned act = __ballot_sync(0xFFFFFFFFu, hm != 0u);
+                    if (act == 0u) break;
+                    if (qn + __popc(act) > K2_QCAP) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
+                    if (hm) {
+                        const int j = __ffs(hm) - 1;
+                        hm &= hm - 1;
+                        const uint32_t cs_ = (uint32_t)(stream_origin + b * 32 + tt);        // coordinate on the streamed axis
+                        const uint32_t cr_ = (uint32_t)(row0 + (gbase + j) * 32 + L);         // coordinate on the row axis
+                        queue[qn + __popc(act & ((1u << lane) - 1u))] = make_uint2(cs_ | (ve & 0xC0000000u), cr_);
+                    }
+                    qn += __popc(act);
                 }
-                qn += __popc(act);
             }
         }
     }
