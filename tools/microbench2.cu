@@ -177,6 +177,51 @@ __global__ void __launch_bounds__(128) k_horner(const uint32_t* in, uint32_t* ou
     if (found) out[0] = found;
 }
 
+// ---- V4 (stream word first in every instruction: operand-reuse cache friendly): mixed ISETP rows + monic degree-D polynomials by Horner (IMAD on the fma pipe) ---------------
+template <int NI, int NP, int D>
+__global__ void __launch_bounds__(128) k_horner_a(const uint32_t* in, uint32_t* out, int reps) {
+    __shared__ __align__(16) uint32_t s[4][TS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = lane; i < TS; i += 32) s[warp][i] = in[(i * 7 + warp) & 4095] | 1u;
+    uint32_t r[NI], c[NP][D];
+    #pragma unroll
+    for (int q = 0; q < NI; ++q) r[q] = in[(threadIdx.x * NI + q + 3 * blockIdx.x) & 4095] & ~1u;
+    #pragma unroll
+    for (int p = 0; p < NP; ++p)
+        #pragma unroll
+        for (int q = 0; q < D; ++q) c[p][q] = in[(threadIdx.x * 16 + p * D + q + 5 * blockIdx.x) & 4095] | 1u;
+    __syncwarp();
+    uint32_t found = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+        for (int b = 0; b < TS / 32; ++b) {
+            const uint32_t* sblk = s[warp] + b * 32;
+            bool p0 = false, p1 = false, p2 = false, p3 = false;
+            #pragma unroll
+            for (int jj = 0; jj < 32; jj += 4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(sblk + jj);
+                const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+                #pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    uint32_t acc[NP];
+                    #pragma unroll
+                    for (int p = 0; p < NP; ++p) acc[p] = vw[e] + c[p][0];
+                    #pragma unroll
+                    for (int q = 1; q < D; ++q)
+                        #pragma unroll
+                        for (int p = 0; p < NP; ++p) acc[p] = vw[e] * acc[p] + c[p][q];
+                    #pragma unroll
+                    for (int q = 0; q < NI; q += 2) { p0 |= (vw[e] == r[q]); p1 |= (vw[e] == r[q + 1]); }
+                    #pragma unroll
+                    for (int p = 0; p < NP; ++p) { if (p & 1) p3 |= (acc[p] == 0); else p2 |= (acc[p] == 0); }
+                }
+            }
+            unsigned mask = __ballot_sync(0xFFFFFFFFu, p0 | p1 | p2 | p3);
+            if (mask) found += __popc(mask);
+        }
+    }
+    if (found) out[0] = found;
+}
+
 template <typename K>
 void run(const char* name, K kern, const uint32_t* in, uint32_t* out, double rows, int sm, int ctas_per_sm) {
     const int grid = sm * ctas_per_sm, reps = 64;
@@ -204,7 +249,7 @@ int main() {
     uint32_t x = 12345;
     for (int i = 0; i < 4096; ++i) { x = x * 1664525u + 1013904223u; h[i] = (x >> 2) & 0x3FFFFFFFu; }
     uint32_t *in, *out; cudaMalloc(&in, sizeof(h)); cudaMalloc(&out, 64); cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
-    for (int c : {4, 6, 8}) {
+    for (int c : {4, 5}) {
         run("isetp R=16", k_isetp<16>, in, out, 16, sm, c);
         run("isetp R=32", k_isetp<32>, in, out, 32, sm, c);
         run("hset2 NH=8  (16 rows)", k_hset2<8>, in, out, 16, sm, c);
@@ -217,6 +262,10 @@ int main() {
         run("horner NI=14 + 2 x deg 8 (30 rows)", k_horner<14, 2, 8>, in, out, 30, sm, c);
         run("horner NI=12 + 2 x deg 9 (30 rows)", k_horner<12, 2, 9>, in, out, 30, sm, c);
         run("horner NI=20 + 3 x deg 8 (44 rows)", k_horner<20, 3, 8>, in, out, 44, sm, c);
+        run("horner-A NI=14 + 2 x deg 8 (30 rows)", k_horner_a<14, 2, 8>, in, out, 30, sm, c);
+        run("horner-A NI=16 + 2 x deg 8 (32 rows)", k_horner_a<16, 2, 8>, in, out, 32, sm, c);
+        run("horner-A NI=12 + 2 x deg 8 (28 rows)", k_horner_a<12, 2, 8>, in, out, 28, sm, c);
+        run("horner-A NI=20 + 3 x deg 8 (44 rows)", k_horner_a<20, 3, 8>, in, out, 44, sm, c);
     }
     return 0;
 }

@@ -670,9 +670,9 @@ __global__ void __launch_bounds__(256) k_int_peak(const uint32_t* __restrict__ i
         // both integer pipes at once: 16 independent LOP3 chains (alu pipe) + 16 independent IMAD chains (fma pipe)
         for (int it = 0; it < iters; ++it) {
             #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                r[q] = (r[q] ^ v) & (r[(q + 1) & 15] | v);
-                r[16 + q] = r[16 + q] * v + r[16 + ((q + 3) & 15)];
+            for (int q = 0; q < 16; ++q) {                 // shared operand first: served by the operand-reuse cache
+                r[q] = (v ^ r[q]) & (v | r[(q + 1) & 15]);
+                r[16 + q] = v * r[16 + q] + r[16 + ((q + 3) & 15)];
             }
             v += 0x9E3779B9u;
         }
