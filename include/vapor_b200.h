@@ -166,7 +166,8 @@ int vapor_gpu_host_free(void* p);
 /* Integer-issue microbenchmark used as the roofline denominator of the tile kernel:
  * which = 0: 32-bit compare-accumulate (ISETP) lane-ops/s, 1: LOP3 lane-ops/s, 2: IADD3 lane-ops/s (alu pipe alone),
  * 3: independent LOP3 + IMAD streams (alu pipe + fma pipe together: the dual-pipe integer issue rate the tile
- * kernel's inner loop is written for). */
+ * kernel's inner loop is written for), 4: the tile kernel's own pair -- ISETP compare-accumulate + IMAD Horner step
+ * with the shared word as first source operand -- and nothing else in the loop. */
 int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s);
 
 /* The hit checksum mixer (host-callable; same function the kernels use). */

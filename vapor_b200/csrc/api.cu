@@ -81,7 +81,7 @@ struct Handle {
     std::string err;
     int64_t hit_budget = 0;          // bytes; 0 = default
     int k2_ctas_per_sm = 0;          // persistent-grid size of kernel 2 = this x SM count; 0 = occupancy
-    int k2_occupancy[K2_NVARIANT] = {0, 0, 0};
+    int k2_occupancy[K2_NVARIANT] = {0, 0, 0, 0, 0};
     int tile_variant = 1;            // k2 inner-loop variant (k2_variant_*), fixed at upload
     int plan_variant = 1;            // variant the resident plan's strips were cut for
 
@@ -445,6 +445,8 @@ void launch_k2(Handle* h, const K2Params& kp) {
     switch (h->plan_variant) {
         case 0:  launch_k2_variant<0>(h, kp); break;
         case 2:  launch_k2_variant<2>(h, kp); break;
+        case 3:  launch_k2_variant<3>(h, kp); break;
+        case 4:  launch_k2_variant<4>(h, kp); break;
         default: launch_k2_variant<1>(h, kp); break;
     }
 }
@@ -666,13 +668,27 @@ __global__ void __launch_bounds__(256) k_int_peak(const uint32_t* __restrict__ i
         #pragma unroll
         for (int q = 0; q < 32; ++q) a ^= r[q];
         if (a == 0x12345678u) out[0] = a;
+    } else if (WHICH == 4) {
+        // the tile kernel's own instruction pair: 16 compare-accumulates (alu pipe) + 16 Horner steps (fma pipe) per
+        // shared word, the shared word first in every instruction (operand-reuse cache), nothing else in the loop
+        bool p0 = false, p1 = false;
+        uint32_t a0 = r[16], a1 = r[17];
+        for (int it = 0; it < iters; ++it) {
+            #pragma unroll
+            for (int q = 0; q < 16; q += 2) {
+                p0 |= (v == r[q]); p1 |= (v == r[q + 1]);
+                a0 = v * a0 + r[18 + (q >> 1)]; a1 = v * a1 + r[26 - (q >> 1)];
+            }
+            v += 0x9E3779B9u;
+        }
+        if (p0 | p1 | (a0 == 0x12345678u) | (a1 == 0x9ABCDEF0u)) out[0] = v;
     } else if (WHICH == 3) {
         // both integer pipes at once: 16 independent LOP3 chains (alu pipe) + 16 independent IMAD chains (fma pipe)
         for (int it = 0; it < iters; ++it) {
             #pragma unroll
-            for (int q = 0; q < 16; ++q) {                 // shared operand first: served by the operand-reuse cache
-                r[q] = (v ^ r[q]) & (v | r[(q + 1) & 15]);
-                r[16 + q] = v * r[16 + q] + r[16 + ((q + 3) & 15)];
+            for (int q = 0; q < 16; ++q) {
+                r[q] = (r[q] ^ v) & (r[(q + 1) & 15] | v);
+                r[16 + q] = r[16 + q] * v + r[16 + ((q + 3) & 15)];
             }
             v += 0x9E3779B9u;
         }
@@ -970,7 +986,7 @@ int vapor_gpu_host_free(void* p) {
 }
 
 int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s) {
-    if (!handle || !lane_ops_per_s || which < 0 || which > 3) return VAPOR_E_ARG;
+    if (!handle || !lane_ops_per_s || which < 0 || which > 4) return VAPOR_E_ARG;
     Handle* h = static_cast<Handle*>(handle);
     CK(cudaSetDevice(h->device));
     DevBuf<uint32_t> in, out;
@@ -987,6 +1003,7 @@ int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s) {
         if (which == 0) k_int_peak<0><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         else if (which == 1) k_int_peak<1><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         else if (which == 3) k_int_peak<3><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
+        else if (which == 4) k_int_peak<4><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         else k_int_peak<2><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         CK(cudaEventRecord(b, h->stream));
         CK(cudaStreamSynchronize(h->stream));

@@ -44,8 +44,8 @@ constexpr int K2_QCAP    = 64;                 // per-warp queue of matched cell
 constexpr int K2_NCAP    = 192;                // per-warp list of candidate notes awaiting resolution
 
 // tile variants: (rows by ISETP, row polynomials).  Variant 1 is the product default.
-constexpr int K2_NVARIANT = 3;
-__host__ __device__ constexpr int k2_variant_ni(int v) { return v == 0 ? 16 : (v == 1 ? 14 : 16); }
+constexpr int K2_NVARIANT = 5;
+__host__ __device__ constexpr int k2_variant_ni(int v) { return v == 0 ? 16 : (v == 1 ? 14 : (v == 2 ? 16 : (v == 3 ? 12 : 10))); }
 __host__ __device__ constexpr int k2_variant_np(int v) { return v == 0 ? 0 : 2; }
 __host__ __device__ constexpr int k2_variant_rows(int v) { return 32 * (k2_variant_ni(v) + K2_D * k2_variant_np(v)); }
 
