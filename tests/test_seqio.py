@@ -1,0 +1,77 @@
+"""In-process FASTA / SAM / BAM access (vapor_b200/seqio.py) -- the stand-in for the reference's
+``samtools faidx`` and ``samtools view`` subprocesses (Simple_function.pyx:1206, :340)."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from vapor_b200 import seqio
+
+import bam_writer
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASE = os.path.join(HERE, "golden", "cli_case")
+
+
+def test_fasta_fetch_matches_plain_slicing(tmp_path):
+    rng = np.random.default_rng(3)
+    seqs = {"chrA": "".join(rng.choice(list("ACGTN"), size=1234)), "chrB": "".join(rng.choice(list("acgt"), size=77)), "c3": "ACGT"}
+    fa = tmp_path / "t.fa"
+    with open(fa, "w") as f:
+        for (name, s), w in zip(seqs.items(), (60, 10, 80)):
+            f.write(f">{name} some description\n")
+            for i in range(0, len(s), w):
+                f.write(s[i:i + w] + "\n")
+    ff = seqio.FastaFile(str(fa))
+    assert os.path.exists(str(fa) + ".fai")
+    for name, s in seqs.items():
+        for a, b in [(1, len(s)), (1, 1), (5, 64), (60, 61), (61, 120), (len(s), len(s)), (len(s) - 3, len(s) + 50), (-5, 10), (0, 3)]:
+            exp = s[max(a, 1) - 1:min(b, len(s))]
+            assert ff.fetch(name, a, b) == exp, (name, a, b)
+    assert ff.fetch("nope", 1, 10) == "" and ff.fetch("chrA", 50, 40) == ""
+    assert seqio.faidx(str(fa), "chrA", 11, 20) == seqs["chrA"][10:20]
+
+
+def _sam_records():
+    recs = []
+    with gzip.open(os.path.join(CASE, "reads.sam.gz"), "rt") as f:
+        for line in f:
+            if line.startswith("@"):
+                continue
+            p = line.rstrip("\n").split("\t")
+            recs.append((p[0], 0, int(p[3]), p[5], p[9]))
+    return recs
+
+
+def test_bam_reader_matches_sam_text(tmp_path):
+    recs = _sam_records()[:900]
+    chrom_len = int(open(os.path.join(CASE, "ref.fa.fai")).read().split()[1])
+    sam = seqio.AlignmentFile(os.path.join(CASE, "reads.sam.gz"))
+    sam_names = {r[0] for r in recs}
+    rng = np.random.default_rng(5)
+    hi = max(r[2] for r in recs)
+    regions = [(1, 500), (hi - 10, hi + 5000), (13000, 13000)] + [tuple(sorted(rng.integers(1, hi + 2000, size=2))) for _ in range(40)]
+    for with_bai in (True, False):
+        bam = str(tmp_path / f"r_{int(with_bai)}.bam")
+        bam_writer.write_bam(bam, [("chr1", chrom_len)], recs, with_bai=with_bai)
+        bf = seqio.AlignmentFile(bam)
+        assert (bf._impl.bai is not None) == with_bai
+        for a, b in regions:
+            exp = [(r.qname, r.pos, r.cigar, r.seq) for r in sam.fetch("chr1", int(a), int(b)) if r.qname in sam_names]
+            got = [(r.qname, r.pos, r.cigar, r.seq) for r in bf.fetch("chr1", int(a), int(b))]
+            assert got == exp, (with_bai, a, b, len(got), len(exp))
+        assert list(bf.fetch("chrZ", 1, 100)) == []
+
+
+def test_chop_reads_same_from_bam_and_sam(tmp_path):
+    """chop_pacbio_read_by_pos (Simple_function.pyx:339-354) gives the same kernel inputs whichever container holds the reads."""
+    from vapor_b200 import Simple_function as SF
+    recs = _sam_records()
+    chrom_len = int(open(os.path.join(CASE, "ref.fa.fai")).read().split()[1])
+    bam = str(tmp_path / "all.bam")
+    bam_writer.write_bam(bam, [("chr1", chrom_len)], recs)
+    for s, e in [(12000 - 500, 12643 + 500), (24714 - 500, 25480 + 500), (36564 - 500, 36564 + 500)]:
+        a = SF.chop_pacbio_read_by_pos(os.path.join(CASE, "reads.sam.gz"), "chr1", s, e, 500)
+        b = SF.chop_pacbio_read_by_pos(bam, "chr1", s, e, 500)
+        assert a == b and len(a) > 3
