@@ -115,8 +115,8 @@ const char* vapor_gpu_last_error(void* handle);   /* handle may be NULL: last op
 /* Tunables: hit-buffer budget in bytes (0 = default) -- bounds device memory per wave. */
 int vapor_gpu_set_hit_budget(void* handle, int64_t bytes);
 /* Named tunables (none changes a result): "hit_budget_bytes", "tile_variant" (inner loop of the tile
- * kernel: 0 = 16 rows/lane by ISETP only, 1 = 14 by ISETP + 2 row polynomials by IMAD [default],
- * 2 = 16 + 2 polynomials), "k2_ctas_per_sm" (persistent-grid size).  Takes effect at the next upload. */
+ * kernel: 0 = 16 rows/lane by ISETP only, 1/2/3/4 = 14/16/12/13 rows by ISETP + 2 row polynomials of
+ * 8 rows by IMAD; default 4), "k2_ctas_per_sm" (persistent-grid size).  Takes effect at the next upload. */
 int vapor_gpu_set_option(void* handle, const char* name, int64_t value);
 
 /* Blocking one-shot: host prep + H2D + kernels 1-4 + D2H.
@@ -166,8 +166,8 @@ int vapor_gpu_host_free(void* p);
 /* Integer-issue microbenchmark used as the roofline denominator of the tile kernel:
  * which = 0: 32-bit compare-accumulate (ISETP) lane-ops/s, 1: LOP3 lane-ops/s, 2: IADD3 lane-ops/s (alu pipe alone),
  * 3: independent LOP3 + IMAD streams (alu pipe + fma pipe together: the dual-pipe integer issue rate the tile
- * kernel's inner loop is written for), 4: the tile kernel's own pair -- ISETP compare-accumulate + IMAD Horner step
- * with the shared word as first source operand -- and nothing else in the loop. */
+ * kernel's inner loop is written for), 4: the tile kernel's inner loop in isolation (14 ISETP + 16 IMAD + 2 zero tests
+ * per shared word, LDS.128 + one vote per 32 words, nothing else): integer lane-instructions/s. */
 int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s);
 
 /* The hit checksum mixer (host-callable; same function the kernels use). */

@@ -82,8 +82,8 @@ struct Handle {
     int64_t hit_budget = 0;          // bytes; 0 = default
     int k2_ctas_per_sm = 0;          // persistent-grid size of kernel 2 = this x SM count; 0 = occupancy
     int k2_occupancy[K2_NVARIANT] = {0, 0, 0, 0, 0};
-    int tile_variant = 1;            // k2 inner-loop variant (k2_variant_*), fixed at upload
-    int plan_variant = 1;            // variant the resident plan's strips were cut for
+    int tile_variant = 4;            // k2 inner-loop variant (k2_variant_*), fixed at upload
+    int plan_variant = 4;            // variant the resident plan's strips were cut for
 
     // plan (host)
     std::vector<Operand> ops;
@@ -446,8 +446,8 @@ void launch_k2(Handle* h, const K2Params& kp) {
         case 0:  launch_k2_variant<0>(h, kp); break;
         case 2:  launch_k2_variant<2>(h, kp); break;
         case 3:  launch_k2_variant<3>(h, kp); break;
-        case 4:  launch_k2_variant<4>(h, kp); break;
-        default: launch_k2_variant<1>(h, kp); break;
+        case 1:  launch_k2_variant<1>(h, kp); break;
+        default: launch_k2_variant<4>(h, kp); break;
     }
 }
 
@@ -668,20 +668,6 @@ __global__ void __launch_bounds__(256) k_int_peak(const uint32_t* __restrict__ i
         #pragma unroll
         for (int q = 0; q < 32; ++q) a ^= r[q];
         if (a == 0x12345678u) out[0] = a;
-    } else if (WHICH == 4) {
-        // the tile kernel's own instruction pair: 16 compare-accumulates (alu pipe) + 16 Horner steps (fma pipe) per
-        // shared word, the shared word first in every instruction (operand-reuse cache), nothing else in the loop
-        bool p0 = false, p1 = false;
-        uint32_t a0 = r[16], a1 = r[17];
-        for (int it = 0; it < iters; ++it) {
-            #pragma unroll
-            for (int q = 0; q < 16; q += 2) {
-                p0 |= (v == r[q]); p1 |= (v == r[q + 1]);
-                a0 = v * a0 + r[18 + (q >> 1)]; a1 = v * a1 + r[26 - (q >> 1)];
-            }
-            v += 0x9E3779B9u;
-        }
-        if (p0 | p1 | (a0 == 0x12345678u) | (a1 == 0x9ABCDEF0u)) out[0] = v;
     } else if (WHICH == 3) {
         // both integer pipes at once: 16 independent LOP3 chains (alu pipe) + 16 independent IMAD chains (fma pipe)
         for (int it = 0; it < iters; ++it) {
@@ -707,6 +693,48 @@ __global__ void __launch_bounds__(256) k_int_peak(const uint32_t* __restrict__ i
         for (int q = 0; q < 32; ++q) a ^= r[q];
         if (a == 0x12345678u) out[0] = a;
     }
+}
+
+// The tile kernel's inner loop in isolation (no queue, no TMA, no exact path): 14 compare-accumulates (alu pipe) +
+// 2 x 8 Horner steps (fma pipe) + 2 zero tests per shared word, words fetched with LDS.128, one vote per 32 words,
+// the shared word first in every instruction.  32 integer instructions per lane and word.
+__global__ void __launch_bounds__(128) k_tile_loop_peak(const uint32_t* __restrict__ in, uint32_t* out, int reps) {
+    __shared__ __align__(16) uint32_t s[4][2048];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = lane; i < 2048; i += 32) s[warp][i] = in[(i * 7 + warp) & 1023] | 1u;
+    uint32_t r[14], c[2][8];
+    #pragma unroll
+    for (int q = 0; q < 14; ++q) r[q] = in[(threadIdx.x * 14 + q + 3 * blockIdx.x) & 1023] & ~1u;
+    #pragma unroll
+    for (int p = 0; p < 2; ++p)
+        #pragma unroll
+        for (int q = 0; q < 8; ++q) c[p][q] = in[(threadIdx.x * 16 + p * 8 + q + 5 * blockIdx.x) & 1023] | 1u;
+    __syncwarp();
+    uint32_t found = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+        for (int b = 0; b < 2048 / 32; ++b) {
+            const uint32_t* sblk = s[warp] + b * 32;
+            bool p0 = false, p1 = false, p2 = false, p3 = false;
+            #pragma unroll
+            for (int jj = 0; jj < 32; jj += 4) {
+                const uint4 v4 = *reinterpret_cast<const uint4*>(sblk + jj);
+                const uint32_t vw[4] = {v4.x, v4.y, v4.z, v4.w};
+                #pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t v = vw[e];
+                    uint32_t a0 = v + c[0][0], a1 = v + c[1][0];
+                    #pragma unroll
+                    for (int q = 1; q < 8; ++q) { a0 = v * a0 + c[0][q]; a1 = v * a1 + c[1][q]; }
+                    #pragma unroll
+                    for (int q = 0; q < 14; q += 2) { p0 |= (v == r[q]); p1 |= (v == r[q + 1]); }
+                    p2 |= (a0 == 0u); p3 |= (a1 == 0u);
+                }
+            }
+            const unsigned mask = __ballot_sync(0xFFFFFFFFu, p0 | p1 | p2 | p3);
+            if (mask) found += __popc(mask);
+        }
+    }
+    if (found) out[0] = found;
 }
 
 }  // namespace
@@ -1000,15 +1028,19 @@ int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s) {
     double best = 0;
     for (int rep = 0; rep < 4; ++rep) {
         CK(cudaEventRecord(a, h->stream));
+        double ops = (double)grid * 256.0 * (double)iters * 32.0;
         if (which == 0) k_int_peak<0><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         else if (which == 1) k_int_peak<1><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         else if (which == 3) k_int_peak<3><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
-        else if (which == 4) k_int_peak<4><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
+        else if (which == 4) {
+            const int g4 = h->sm_count * 4, reps = 48;
+            k_tile_loop_peak<<<g4, 128, 0, h->stream>>>(in.p, out.p, reps);
+            ops = (double)g4 * 128.0 * (double)reps * 2048.0 * 32.0;          // 32 integer instructions per lane and word
+        }
         else k_int_peak<2><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         CK(cudaEventRecord(b, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         float ms = 0; cudaEventElapsedTime(&ms, a, b);
-        const double ops = (double)grid * 256.0 * (double)iters * 32.0;
         if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
     }
     cudaEventDestroy(a); cudaEventDestroy(b);

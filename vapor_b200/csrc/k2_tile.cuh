@@ -43,9 +43,11 @@ constexpr int K2_SBUF    = K2_TS + 40;         // words per warp buffer (alignme
 constexpr int K2_QCAP    = 64;                 // per-warp queue of matched cells awaiting emission
 constexpr int K2_NCAP    = 192;                // per-warp list of candidate notes awaiting resolution
 
-// tile variants: (rows by ISETP, row polynomials).  Variant 1 is the product default.
+// tile variants: (rows by ISETP, row polynomials): 0 = (16,0), 1 = (14,2), 2 = (16,2), 3 = (12,2), 4 = (13,2).
+// Variant 4 is the product default: with the exact path and loop overhead also on the alu pipe, 13 + 2 compares
+// against 16 multiply-adds per streamed word balances the two pipes best (measured).
 constexpr int K2_NVARIANT = 5;
-__host__ __device__ constexpr int k2_variant_ni(int v) { return v == 0 ? 16 : (v == 1 ? 14 : (v == 2 ? 16 : (v == 3 ? 12 : 10))); }
+__host__ __device__ constexpr int k2_variant_ni(int v) { return v == 0 ? 16 : (v == 1 ? 14 : (v == 2 ? 16 : (v == 3 ? 12 : 13))); }
 __host__ __device__ constexpr int k2_variant_np(int v) { return v == 0 ? 0 : 2; }
 __host__ __device__ constexpr int k2_variant_rows(int v) { return 32 * (k2_variant_ni(v) + K2_D * k2_variant_np(v)); }
 
@@ -254,7 +256,7 @@ k2_tile_match(const K2Params p)
 {
     constexpr int R = NI + K2_D * NP;              // rows per lane; row q of lane l is strip row q*32 + l
     constexpr int ROWS = 32 * R;
-    static_assert(NI % 2 == 0 && NP <= 2 && R <= 32, "row split");
+    static_assert(NP <= 2 && R <= 32, "row split");
     __shared__ __align__(16) uint32_t s_buf[K2_WARPS][K2_SBUF];
     __shared__ __align__(8) uint64_t s_bar[K2_WARPS];
     __shared__ __align__(8) uint2 s_queue[K2_WARPS][K2_QCAP];
@@ -393,7 +395,10 @@ k2_tile_match(const K2Params p)
                         #pragma unroll
                         for (int g = 0; g < NP; ++g) acc[g] = v * acc[g] + c[g][i];
                     #pragma unroll
-                    for (int q = 0; q < NI / 2; ++q) { pi0 |= (v == r[q]); pi1 |= (v == r[NI / 2 + q]); }
+                    for (int q = 0; q < NI - NI / 2; ++q) {
+                        if (q < NI / 2) pi0 |= (v == r[q]);
+                        pi1 |= (v == r[NI / 2 + q]);
+                    }
                     if (NP > 0) pg0 |= (acc[0] == 0u);
                     if (NP > 1) pg1 |= (acc[NP > 1 ? 1 : 0] == 0u);
                 }
