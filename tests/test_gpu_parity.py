@@ -232,3 +232,15 @@ def test_properties_at_benchmark_scale(engine):
     exp = BO.score_batch(sample)
     got = engine.score(sample)
     _compare(got, exp)
+
+
+def test_pipeline_double_buffered(engine):
+    """engine.Pipeline: several batches through two handles give the same results as one handle, in order."""
+    from vapor_b200.engine import Pipeline
+    ws = [synth.make_workload(6, seed=100 + i, size_range=(50, 900), reads_per_sv=5) for i in range(5)]
+    exp = [engine.score(w.batch) for w in ws]
+    with Pipeline(0, depth=2) as pipe:
+        got = pipe.map([w.batch for w in ws])
+    for g, e in zip(got, exp):
+        for f in e.__dataclass_fields__:
+            np.testing.assert_array_equal(getattr(g, f), getattr(e, f), err_msg=f)

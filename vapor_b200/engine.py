@@ -347,6 +347,63 @@ class Engine:
         return v.value
 
 
+class Pipeline:
+    """Double-buffered scoring of a stream of batches on one GPU: ``depth`` handles (``vapor_gpu_open`` each, own
+    stream and device buffers), one worker thread per handle.  While one handle's kernels run, the next batch is
+    planned on the host and copied in on another handle, so host planning + H2D hide under the kernels
+    (the C-ABI call releases the GIL).  Results come back in submission order.
+
+        with Pipeline(device=0, depth=2) as pipe:
+            for res in pipe.map(batches): ...
+    """
+
+    def __init__(self, device: int = 0, depth: int = 2, options: Optional[dict] = None):
+        self.engines = [Engine(device) for _ in range(max(1, depth))]
+        for e in self.engines:
+            for k, v in (options or {}).items():
+                e.set_option(k, v)
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+    def __enter__(self): return self
+    def __exit__(self, *a): self.close()
+
+    def map(self, batches, results: Optional[Sequence[Optional[Results]]] = None):
+        """Score every batch; ``results[i]`` (optional) is a caller-provided (e.g. pinned) Results to fill."""
+        import queue
+        import threading
+        batches = list(batches)
+        n = len(batches)
+        out: List[Optional[Results]] = [None] * n
+        errs: List[BaseException] = []
+        nxt = [0]
+        lock = threading.Lock()
+
+        def work(eng):
+            while True:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= n or errs:
+                    return
+                try:
+                    into = results[i] if results is not None and results[i] is not None else _alloc_results(batches[i].n_task, batches[i].n_sv)
+                    out[i] = eng.score_into(batches[i], into)
+                except BaseException as e:          # noqa: BLE001
+                    errs.append(e)
+                    return
+        th = [threading.Thread(target=work, args=(e,)) for e in self.engines]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out
+
+
 def hit_mix(x, y) -> np.ndarray:
     """numpy twin of ``vapor_hit_mix`` (include/vapor_b200.h) for checksum comparisons."""
     x = np.asarray(x, dtype=np.uint64)
