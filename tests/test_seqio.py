@@ -75,3 +75,21 @@ def test_chop_reads_same_from_bam_and_sam(tmp_path):
         a = SF.chop_pacbio_read_by_pos(os.path.join(CASE, "reads.sam.gz"), "chr1", s, e, 500)
         b = SF.chop_pacbio_read_by_pos(bam, "chr1", s, e, 500)
         assert a == b and len(a) > 3
+
+
+def test_cigar_table_walk_equals_plain_walk():
+    """The table-driven cigar2alignstart_by_pos equals the reference's op-by-op loop (Simple_function.pyx:309-337) on
+    random CIGARs, including X / N / H / P operations, windows before the alignment and beyond its end."""
+    from vapor_b200 import Simple_function as SF
+    rng = np.random.default_rng(8)
+    for _ in range(300):
+        n_ops = int(rng.integers(1, 60))
+        ops = rng.choice(list("MIDNSHP=X"), size=n_ops, p=[0.4, 0.15, 0.15, 0.02, 0.05, 0.02, 0.01, 0.1, 0.1])
+        cigar = "".join(f"{int(rng.integers(1, 40))}{o}" for o in ops)
+        a0 = int(rng.integers(1, 5000))
+        for start in (a0 - 10, a0, a0 + 1, a0 + int(rng.integers(0, 600)), a0 + 100000):
+            rr, ar, last = SF._cigar_walk(cigar, a0, start)
+            sd = ar - start
+            exp = [rr - sd, 0] if (last != "" and last in "M=") else [rr, sd]
+            assert SF.cigar2alignstart_by_pos(cigar, a0, start, start + 1000) == exp, (cigar, a0, start)
+    assert SF.cigar2alignstart_by_pos("*", 10, 20, 30) == [0, -10]

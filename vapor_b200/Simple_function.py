@@ -240,9 +240,9 @@ def ref_seq_readin(ref, chrom, start, end, reverse_flag="FALSE"):
 _CIGAR = re.compile(r"(\d+)([MIDNSHP=X])")
 
 
-def cigar2alignstart_by_pos(cigar, align_start, start, end):
-    """Walk the CIGAR up to reference position ``start``: returns [read offset, missed bases]
-    (Simple_function.pyx:309-337).  # quirk: X, N, H, P advance nothing."""
+def _cigar_walk(cigar, align_start, start):
+    """The reference's loop, op by op (Simple_function.pyx:316-330): the definition the table-driven version below
+    is tested against."""
     read_rec, align_rec = 0, align_start
     last = ""
     for m in _CIGAR.finditer(cigar):
@@ -259,6 +259,59 @@ def cigar2alignstart_by_pos(cigar, align_start, start, end):
         last = op
         if align_rec > start - 1:
             break
+    return read_rec, align_rec, last
+
+
+_READ_ADV = np.zeros(256, dtype=np.int64)
+_REF_ADV = np.zeros(256, dtype=np.int64)
+for _c in "SM=I":
+    _READ_ADV[ord(_c)] = 1
+for _c in "M=D":
+    _REF_ADV[ord(_c)] = 1
+_cigar_tables: Dict[str, tuple] = {}
+
+
+def _cigar_table(cigar):
+    """(ops, cumulative read advance, cumulative reference advance) of a CIGAR string, parsed once with numpy and
+    cached: a CLR read has thousands of operations and is queried by several windows."""
+    t = _cigar_tables.get(cigar)
+    if t is None:
+        b = np.frombuffer(cigar.encode("latin-1"), dtype=np.uint8)
+        is_op = np.isin(b, np.frombuffer(b"MIDNSHP=X", dtype=np.uint8))
+        idx = np.nonzero(is_op)[0]
+        if len(idx) == 0 or not np.all((b[~is_op] >= 48) & (b[~is_op] <= 57)):
+            t = None if len(idx) == 0 else False
+        if t is None and len(idx):
+            starts = np.concatenate([[0], idx[:-1] + 1])
+            ndig = idx - starts
+            if (ndig <= 0).any() or (ndig > 18).any():
+                t = False
+            else:
+                owner = np.repeat(np.arange(len(idx)), ndig)
+                dig_pos = np.nonzero(~is_op)[0]
+                power = idx[owner] - dig_pos - 1
+                lens = np.zeros(len(idx), dtype=np.int64)
+                np.add.at(lens, owner, (b[dig_pos].astype(np.int64) - 48) * 10 ** power.astype(np.int64))
+                ops = b[idx]
+                t = (ops, np.cumsum(lens * _READ_ADV[ops]), np.cumsum(lens * _REF_ADV[ops]))
+        if len(_cigar_tables) > 200000:
+            _cigar_tables.clear()
+        _cigar_tables[cigar] = t
+    return t
+
+
+def cigar2alignstart_by_pos(cigar, align_start, start, end):
+    """Walk the CIGAR up to reference position ``start``: returns [read offset, missed bases]
+    (Simple_function.pyx:309-337).  # quirk: X, N, H, P advance nothing."""
+    t = _cigar_table(cigar)
+    if not t:                                   # '*', empty or malformed: the plain walk defines the answer
+        read_rec, align_rec, last = _cigar_walk(cigar, align_start, start)
+    else:
+        ops, cum_read, cum_ref = t
+        # first operation after which align_start + cum_ref > start - 1, else the last one
+        i = int(np.searchsorted(cum_ref, start - 1 - align_start, side="right"))
+        i = min(i, len(ops) - 1)
+        read_rec, align_rec, last = int(cum_read[i]), align_start + int(cum_ref[i]), chr(ops[i])
     start_dis = int(align_rec) - start
     if last != "" and last in "M=":
         return [read_rec - start_dis, 0]

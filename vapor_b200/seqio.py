@@ -24,6 +24,7 @@ import re
 import shutil
 import struct
 import subprocess
+import threading
 import zlib
 from typing import Dict, Iterator, List, NamedTuple, Optional, Tuple
 
@@ -53,10 +54,10 @@ class FastaFile:
                 if len(p) >= 5:
                     self.index[p[0]] = (int(p[1]), int(p[2]), int(p[3]), int(p[4]))
                     self.order.append(p[0])
-        self._fh = open(path, "rb")
+        self._fd = os.open(path, os.O_RDONLY)           # positional reads (os.pread): safe from several threads
 
     def close(self):
-        self._fh.close()
+        os.close(self._fd)
 
     def fetch(self, chrom: str, start: int, end: int) -> str:
         """Bases ``start..end`` (1-based, inclusive) of ``chrom``; clipped to the contig like samtools
@@ -72,8 +73,7 @@ class FastaFile:
         s0, e0 = start - 1, end                                   # 0-based half open
         b0 = offset + (s0 // lb) * lw + s0 % lb
         b1 = offset + ((e0 - 1) // lb) * lw + (e0 - 1) % lb + 1
-        self._fh.seek(b0)
-        raw = self._fh.read(b1 - b0)
+        raw = os.pread(self._fd, b1 - b0, b0)
         return raw.replace(b"\n", b"").replace(b"\r", b"").decode("latin-1")
 
 
@@ -360,7 +360,7 @@ class AlignmentFile:
 
 
 _fasta_cache: Dict[str, FastaFile] = {}
-_aln_cache: Dict[str, AlignmentFile] = {}
+_aln_cache: Dict[object, AlignmentFile] = {}
 
 
 def fasta(path: str) -> FastaFile:
@@ -370,9 +370,17 @@ def fasta(path: str) -> FastaFile:
 
 
 def alignments(path: str) -> AlignmentFile:
-    if path not in _aln_cache:
-        _aln_cache[path] = AlignmentFile(path)
-    return _aln_cache[path]
+    """Cached reader.  SAM text is an immutable in-memory index shared by all threads; a BAM reader keeps a file
+    position and a decompressed block, so every thread gets its own."""
+    a = _aln_cache.get(path)
+    if a is None:
+        a = _aln_cache.setdefault(path, AlignmentFile(path))
+    if isinstance(a._impl, _SamText):
+        return a
+    key = (path, threading.get_ident())
+    if key not in _aln_cache:
+        _aln_cache[key] = AlignmentFile(path)
+    return _aln_cache[key]
 
 
 def faidx(ref: str, chrom: str, start: int, end: int) -> str:
