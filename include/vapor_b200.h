@@ -174,6 +174,7 @@ int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s);
 uint64_t vapor_hit_mix(uint32_t x, uint32_t y);
 
 int vapor_b200_abi_version(void);
+int vapor_gpu_device_count(void);     /* CUDA devices visible to this process (0 without a driver) */
 
 #ifdef __cplusplus
 }

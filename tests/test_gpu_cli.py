@@ -80,3 +80,20 @@ def test_two_sessions_same_output(tmp_path, engine):
                 s.close()
         outs.append(open(out).read())
     assert outs[0] == outs[1]
+
+
+def test_worker_processes_same_output(tmp_path):
+    """`--gpus N` runs one worker process per GPU (here 2 workers sharing the one GPU): byte-identical table."""
+    import subprocess
+    import sys
+    root = os.path.dirname(CC.HERE)
+    outs = []
+    for n in (1, 2):
+        out = os.path.join(str(tmp_path), f"bed_p{n}.vapor")
+        subprocess.run([sys.executable, os.path.join(root, "bin", "vapor"), "bed", "--sv-input", os.path.join(CC.CASE, "svs.bed"),
+                        "--output-path", os.path.join(str(tmp_path), "figs"), "--output-file", out,
+                        "--reference", os.path.join(CC.CASE, "ref.fa"), "--pacbio-input", os.path.join(CC.CASE, "reads.sam.gz"),
+                        "--gpus", str(n)], check=True, stdout=subprocess.DEVNULL)
+        outs.append(open(out).read())
+    assert outs[0] == outs[1]
+    CC.compare_bed_tables(os.path.join(str(tmp_path), "bed_p2.vapor"), os.path.join(CC.CASE, "svs.bed.vapor.golden"))

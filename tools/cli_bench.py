@@ -31,8 +31,9 @@ def main():
     t0 = time.perf_counter()
     seqio.fasta(ds.ref_fa); seqio.alignments(ds.sam)            # parse + index once (cached for the run)
     t_load = time.perf_counter() - t0
-    sessions = [SF.Session(d) for d in range(args.gpus)]
-    SF.set_session(sessions[0])
+    sessions = [SF.Session(0)] if args.gpus == 1 else args.gpus          # N > 1: one worker process per GPU
+    if args.gpus == 1:
+        SF.set_session(sessions[0])
 
     class A:
         pass
@@ -44,14 +45,15 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):
         rows = cli.run_bed(a, sessions)
     t_run = time.perf_counter() - t0
-    stats = {k: sum(s.stats[k] for s in sessions) for k in sessions[0].stats}
-    for s in sessions:
-        s.close()
+    stats = {"reads_scored": None}
+    if args.gpus == 1:
+        stats = dict(sessions[0].stats)
+        sessions[0].close()
     called = sum(1 for r in rows if len(r) > 4)
     print(json.dumps({"n_sv": args.n_sv, "gpus": args.gpus, "rows": len(rows), "rows_with_scores": called,
                       "generate_s": round(t_gen, 2), "load_index_s": round(t_load, 2), "vapor_bed_s": round(t_run, 2),
                       "sv_per_s": round(len(rows) / t_run, 1), "reads_scored": stats["reads_scored"],
-                      "reads_per_s": round(stats["reads_scored"] / t_run, 1), "session": stats}))
+                      "reads_per_s": round(stats["reads_scored"] / t_run, 1) if stats["reads_scored"] else None, "session": stats}))
 
 
 if __name__ == "__main__":

@@ -268,6 +268,9 @@ for _c in "SM=I":
     _READ_ADV[ord(_c)] = 1
 for _c in "M=D":
     _REF_ADV[ord(_c)] = 1
+_IS_OP = np.zeros(256, dtype=bool)
+_IS_OP[np.frombuffer(b"MIDNSHP=X", dtype=np.uint8)] = True
+_POW10 = 10 ** np.arange(19, dtype=np.int64)
 _cigar_tables: Dict[str, tuple] = {}
 
 
@@ -277,9 +280,11 @@ def _cigar_table(cigar):
     t = _cigar_tables.get(cigar)
     if t is None:
         b = np.frombuffer(cigar.encode("latin-1"), dtype=np.uint8)
-        is_op = np.isin(b, np.frombuffer(b"MIDNSHP=X", dtype=np.uint8))
+        is_op = _IS_OP[b]
         idx = np.nonzero(is_op)[0]
-        if len(idx) == 0 or not np.all((b[~is_op] >= 48) & (b[~is_op] <= 57)):
+        dig_pos = np.nonzero(~is_op)[0]
+        dig = b[dig_pos].astype(np.int64) - 48
+        if len(idx) == 0 or (dig < 0).any() or (dig > 9).any() or (len(b) and not is_op[-1]):
             t = None if len(idx) == 0 else False
         if t is None and len(idx):
             starts = np.concatenate([[0], idx[:-1] + 1])
@@ -288,10 +293,7 @@ def _cigar_table(cigar):
                 t = False
             else:
                 owner = np.repeat(np.arange(len(idx)), ndig)
-                dig_pos = np.nonzero(~is_op)[0]
-                power = idx[owner] - dig_pos - 1
-                lens = np.zeros(len(idx), dtype=np.int64)
-                np.add.at(lens, owner, (b[dig_pos].astype(np.int64) - 48) * 10 ** power.astype(np.int64))
+                lens = np.add.reduceat(dig * _POW10[idx[owner] - dig_pos - 1], starts - np.arange(len(idx)))
                 ops = b[idx]
                 t = (ops, np.cumsum(lens * _READ_ADV[ops]), np.cumsum(lens * _REF_ADV[ops]))
         if len(_cigar_tables) > 200000:

@@ -173,43 +173,77 @@ def svelter_readin(file_in):
 
 # ---- event list -> rows ---------------------------------------------------------------------------------------
 class Event:
-    """One output row to be: a key, the driver coroutine factory, and how the row is laid out."""
-    __slots__ = ("key", "make", "row_head")
+    """One output row to be: a key, the driver coroutine to run (name in Simple_function + arguments, so that the
+    event can be shipped to a worker process), and how the row is laid out."""
+    __slots__ = ("key", "spec", "row_head")
 
-    def __init__(self, key, make, row_head=None):
-        self.key, self.make, self.row_head = key, make, row_head
+    def __init__(self, key, spec, row_head=None):
+        self.key, self.spec, self.row_head = key, spec, row_head
+
+    def make(self):
+        return getattr(SF, self.spec[0])(*self.spec[1])
 
 
-def score_events(events: Sequence[Event], sessions: Sequence[SF.Session]) -> List[list]:
-    """Run every event's driver, sharded round-robin over the sessions (one per GPU), and summarise.
-    Returns, per event, the row ``result_organize_ins`` + ``gt_estimate_log_likelihood`` would give:
-    ``[key, QS, GS, Rec, GT, GQ]`` or ``[key, 'NA', 'NA', 'NA']``."""
-    n_s = len(sessions)
+def _shard_worker(job):
+    """Worker process of the multi-GPU command line: one process per GPU, its own Session, its share of the events."""
+    device, specs = job
+    from ._native import load
+    sess = SF.Session(device % max(1, load().vapor_gpu_device_count()))      # more workers than GPUs: share them
+    SF.set_session(sess)
+    try:
+        res = sess.run_events([getattr(SF, name)(*a) for name, a in specs])
+        return [r if r is not None else [] for r in res], dict(sess.stats)
+    finally:
+        sess.close()
+        SF.set_session(None)
+
+
+def score_events(events: Sequence[Event], sessions) -> List[list]:
+    """Run every event's driver and summarise.  ``sessions`` is a list of open Sessions (events are sharded
+    round-robin over them, one thread each) or an int N > 1: N worker *processes*, one per GPU -- the host side of
+    the drivers (region extraction, CIGAR walks, string building) is what limits the command line, and processes
+    scale it where threads cannot.  Independent work queues either way; rows come back in input order.
+    Returns, per event, ``[key, QS, GS, Rec, GT, GQ]`` or ``[key, 'NA', 'NA', 'NA']``."""
     score_lists: List[list] = [[] for _ in events]
-    errs: List[BaseException] = []
-
-    def work(si):
+    live = [i for i, e in enumerate(events) if e.spec is not None]
+    if isinstance(sessions, int):
+        n_s = sessions
+        import multiprocessing as mp
+        jobs = [(d, [events[i].spec for i in live[d::n_s]]) for d in range(n_s)]
+        with mp.get_context("fork").Pool(n_s) as pool:          # fork: the parsed FASTA index / SAM records are inherited
+            outs = pool.map(_shard_worker, jobs, chunksize=1)
+        for d, (lists, _stats) in enumerate(outs):
+            for i, r in zip(live[d::n_s], lists):
+                score_lists[i] = r
+        summ_session = SF.Session(0)
         try:
-            SF.set_session(sessions[si], thread_only=True)   # figure hooks use the calling thread's session
-            idx = list(range(si, len(events), n_s))
-            cos = [events[i].make() if events[i].make is not None else None for i in idx]
-            live = [(i, c) for i, c in zip(idx, cos) if c is not None]
-            res = sessions[si].run_events([c for _, c in live])
-            for (i, _), r in zip(live, res):
-                score_lists[i] = r if r is not None else []
-        except BaseException as e:                  # noqa: BLE001
-            errs.append(e)
-    if n_s == 1:
-        work(0)
+            summ = summ_session.summarize(score_lists) if events else []
+        finally:
+            summ_session.close()
     else:
-        th = [threading.Thread(target=work, args=(i,)) for i in range(n_s)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-    if errs:
-        raise errs[0]
-    summ = sessions[0].summarize(score_lists) if events else []
+        n_s = len(sessions)
+        errs: List[BaseException] = []
+
+        def work(si):
+            try:
+                SF.set_session(sessions[si], thread_only=True)   # figure hooks use the calling thread's session
+                idx = live[si::n_s]
+                res = sessions[si].run_events([events[i].make() for i in idx])
+                for i, r in zip(idx, res):
+                    score_lists[i] = r if r is not None else []
+            except BaseException as e:                  # noqa: BLE001
+                errs.append(e)
+        if n_s == 1:
+            work(0)
+        else:
+            th = [threading.Thread(target=work, args=(i,)) for i in range(n_s)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        if errs:
+            raise errs[0]
+        summ = sessions[0].summarize(score_lists) if events else []
     rows = []
     for ev, s in zip(events, summ):
         rows.append([ev.key, "NA", "NA", "NA"] if s is None else [ev.key, s["QS"], s["GS"], s["Rec"], s["GT"], s["GQ"]])
@@ -236,11 +270,11 @@ def run_bed(args, sessions):
     for x in bed_info_readin(args.sv_input, out_path):
         kind = x[-1]
         if kind in ("a/", "/a", "/", "DEL"):
-            label, drv = "DEL", SF.co_simple_del
+            label, drv = "DEL", "co_simple_del"
         elif kind in ("a/a^", "a^/a", "a^/a^", "INV"):
-            label, drv = "INV", SF.co_simple_inv
+            label, drv = "INV", "co_simple_inv"
         elif kind in ("a/aa", "aa/a", "aa/aa", "DUP", "TANDUP"):
-            label, drv = "TANDUP", SF.co_simple_tandup
+            label, drv = "TANDUP", "co_simple_tandup"
         elif kind == "INS":
             label, drv = "INS", None
         else:
@@ -252,11 +286,11 @@ def run_bed(args, sessions):
             ins_pos = "_".join(str(i) for i in x[:2])
             ins_seq = "X" * x[4] if isinstance(x[4], int) else x[4]
             fig = out_path + sample + ".INS." + key.replace(":", "__") + ".png"
-            make = (lambda p=plt_li, ip=ins_pos, s=ins_seq, f=fig: SF.co_simple_ins(cff, p, bam_in, ref, ip, s, f, "+"))
+            make = ("co_simple_ins", (cff, plt_li, bam_in, ref, ins_pos, ins_seq, fig, "+"))
         else:
             key = ":".join(str(i) for i in x[:-3]) + ":" + label
             fig = out_path + sample + "." + label + "." + key.replace(":", "__") + ".png"
-            make = (lambda p=plt_li, sv=x[:-3], f=fig, d=drv: d(cff, p, bam_in, ref, sv, f))
+            make = (drv, (cff, plt_li, bam_in, ref, x[:-3], fig))
         events.append(Event(key, make, row_head=key.split(":") + [x[3]]))
     rows = score_events(events, sessions)
     SF.write_output_initiate(out_name)
@@ -296,27 +330,27 @@ def run_vcf(args, sessions):
                     events.append(Event(":".join(str(i) for i in y + ["DEL"]), None))
                     continue
                 key = ":".join(str(i) for i in y + [cls])
-                drv = SF.co_simple_del if cls == "DEL" else SF.co_simple_inv
-                events.append(Event(key, lambda p=p, y=y, key=key, d=drv, c=cls: d(cff, p, bam_in, ref, y, fig(c, key))))
+                drv = "co_simple_del" if cls == "DEL" else "co_simple_inv"
+                events.append(Event(key, (drv, (cff, p, bam_in, ref, y, fig(cls, key)))))
             elif cls == "INS":
                 key = ":".join(str(i) for i in y[:3] + ["INS"])
                 ins_pos = "_".join(str(i) for i in y[:2])
                 # quirk (vapor_vali/vapor:426-427): y always has 4 items, so a record without SEQ= is scored with an
                 # empty insertion (-> 'NA'), never with the 'X' * SVLEN stand-in the bed path uses
                 ins_seq = y[-1] if len(y) == 4 else "X" * y[2]
-                events.append(Event(key, lambda p=p, ip=ins_pos, s=ins_seq, key=key: SF.co_simple_ins(cff, p, bam_in, ref, ip, s, fig("INS", key), "+")))
+                events.append(Event(key, ("co_simple_ins", (cff, p, bam_in, ref, ins_pos, ins_seq, fig("INS", key), "+"))))
             elif cls == "DISDUP":
                 key = ":".join(str(i) for i in y + ["DISDUP"])
-                events.append(Event(key, lambda p=p, y=y, key=key: SF.co_simple_disdup(cff, p, bam_in, ref, y, fig("DISDUP", key))))
+                events.append(Event(key, ("co_simple_disdup", (cff, p, bam_in, ref, y, fig("DISDUP", key)))))
             elif cls == "DEL_INV":
                 key = ":".join(["_".join(str(i) for i in j) for j in y] + ["DEL_INV"])
-                events.append(Event(key, lambda p=p, y=y, key=key: SF.co_del_inv(cff, p, bam_in, ref, y, fig("DEL_INV", key))))
+                events.append(Event(key, ("co_del_inv", (cff, p, bam_in, ref, y, fig("DEL_INV", key)))))
             elif cls == "DUP_INV":
                 key = ":".join(str(i) for i in y + ["DUP_INV"])
-                events.append(Event(key, lambda p=p, y=y, key=key: SF.co_dup_inv(cff, p, bam_in, ref, y, fig("DUP_INV", key))))
+                events.append(Event(key, ("co_dup_inv", (cff, p, bam_in, ref, y, fig("DUP_INV", key)))))
             elif cls == "Other":
                 key = ":".join(str(i) for i in y + ["CANNOT_CLASSIFY"])
-                events.append(Event(key, lambda p=p, y=y, key=key: SF.co_cannot_classify(cff, p, bam_in, ref, y, fig("CANNOT_CLASSIFY", key))))
+                events.append(Event(key, ("co_cannot_classify", (cff, p, bam_in, ref, y, fig("CANNOT_CLASSIFY", key)))))
     rows = score_events(events, sessions)
     out_name = vcf_input + ".vapor"
     SF.write_output_initiate(out_name)
@@ -344,7 +378,7 @@ def run_svelter(args, sessions):
                 figname = out_path + sample + key.replace(":", "__") + ".png"
                 info = [k1, k2] + k3
                 print(info)
-                events.append(Event(key, lambda p=plt_li, i=info, f=figname: SF.co_cannot_classify(cff, p, bam_in, ref, i, f)))
+                events.append(Event(key, ("co_cannot_classify", (cff, plt_li, bam_in, ref, info, figname))))
     rows = score_events(events, sessions)
     for ev, row in zip(events, rows):
         _write_row(args.output_file, [ev.key], row)
@@ -376,7 +410,16 @@ def main(argv=None):
                      "argument the parser never defines); it is not part of this build")
         prep.print_read_me()
         return 2
-    sessions = [SF.Session(d) for d in range(max(1, args.gpus))]
+    if args.gpus > 1:
+        # one worker process per GPU; parse the inputs once here so the forked workers inherit them, and keep CUDA
+        # out of this process until the workers are done
+        from . import seqio
+        seqio.fasta(args.reference)
+        for b in SF.bam_in_decide(args.pacbio_input, None):
+            seqio.alignments(b)
+        runners[fn](args, args.gpus)
+        return 0
+    sessions = [SF.Session(0)]
     SF.set_session(sessions[0])
     try:
         runners[fn](args, sessions)

@@ -746,6 +746,11 @@ extern "C" {
 
 int vapor_b200_abi_version(void) { return VAPOR_B200_ABI_VERSION; }
 
+int vapor_gpu_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 uint64_t vapor_hit_mix(uint32_t x, uint32_t y) { return hit_mix(x, y); }
 
 const char* vapor_gpu_last_error(void* handle) {
