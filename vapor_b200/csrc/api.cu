@@ -238,7 +238,7 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
         o.n = std::max(0, o.len - k + 1);
         o.hash_off = hash_off; o.code_off = code_off;
         hash_off += align4(o.n) + 8;
-        code_off += o.len + 8;
+        code_off += (o.len + 8 + 15) & ~15;          // 16-byte aligned code strings (8-byte stores in kernel 1)
         h->ops.push_back(o);
         int32_t id = (int32_t)h->ops.size() - 1;
         local.push_back({seq, k, flags, id});
@@ -925,7 +925,7 @@ int vapor_gpu_selfplot_qc(void* handle, const uint8_t* seq_bytes, const int64_t*
         o.seq_begin = seq_off[i]; o.len = (int32_t)L; o.k = k[i]; o.flags = OPF_READ;
         o.n = std::max(0, o.len - o.k + 1);
         o.hash_off = hash_off; o.code_off = code_off;
-        hash_off += align4(o.n) + 8; code_off += o.len + 8;
+        hash_off += align4(o.n) + 8; code_off += (o.len + 8 + 15) & ~15;
         ops[i] = o;
         Plot p{};
         p.read_op = p.struct_op = (int32_t)i; p.miss = 0; p.n = p.m = o.n; p.cap = 0; p.kind = PLOT_QC; p.hit_off = i;

@@ -14,7 +14,10 @@
 //              bit 31 is set and the word is a symmetric hash of (forward, revcomp) that the
 //              tile kernel confirms on the code strings.  Bit 30 marks a k-mer that is its own
 //              reverse complement: the reference appends such a read position twice.
-// HBM-bound: 1 B/base read, 1 B/base + 4 B/position written.
+// HBM-bound: 1 B/base read, 1 B/base + 4 B/position written.  Bases are read with aligned 32-bit loads and turned
+// into codes through a shared-memory copy of the alphabet table; every thread then owns 8 consecutive positions and
+// *rolls* the 2-bit forward / reverse-complement words of its window from one position to the next (k <= 15), so the
+// work per position is O(1), not O(k); results leave as 16-byte (words) and 8-byte (codes) stores.
 #pragma once
 #include "common.cuh"
 
@@ -43,13 +46,40 @@ __host__ __device__ __forceinline__ uint32_t mix30(uint32_t x) {
     return x;
 }
 
+// Word of one k-mer the slow way (k > 15, or a k-mer holding N / lower case): symmetric hash of the forward and the
+// reverse-complement strings, palindromes confirmed exactly.  `w` points at the k codes of the k-mer.
+__device__ __forceinline__ uint32_t k1_hashed_word(const uint8_t* w, int k, bool& pal) {
+    const uint64_t B = 0x9E3779B97F4A7C15ull | 1ull;
+    uint64_t f = 0, r = 0;
+    #pragma unroll 1
+    for (int t = 0; t < k; ++t) {
+        f = f * B + (uint64_t)(w[t] + 1);
+        r = r * B + (uint64_t)(comp_code(w[k - 1 - t]) + 1);
+    }
+    pal = false;
+    if (f == r) {                          // candidate palindrome: confirm exactly
+        pal = true;
+        for (int t = 0; t < k; ++t) pal &= (w[t] == comp_code(w[k - 1 - t]));
+    }
+    const uint64_t cmin = f < r ? f : r, cmax = f < r ? r : f;
+    const uint32_t h30 = (uint32_t)(fmix64(cmin ^ (cmax * 0xD6E8FEB86659FD93ull)) >> 34);
+    uint32_t h = H_NEEDS_VERIFY | (pal ? H_PALINDROME : 0u) | h30;
+    if (h > H_MAX_VALID) h -= 4;
+    return h;
+}
+
+constexpr int K1_RUN = K1_CHUNK / K1_THREADS;      // consecutive positions per thread (8)
+
 __global__ void __launch_bounds__(K1_THREADS)
 k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
               const int32_t* __restrict__ chunk_prefix,   // [n_ops+1] cumulative chunk counts
               int n_ops, uint32_t* __restrict__ hash, uint8_t* __restrict__ code,
               int32_t* __restrict__ op_status)
 {
-    __shared__ uint8_t s_code[K1_CHUNK + K1_MAXK + 8];
+    __shared__ uint8_t s_lut[256];                               // the alphabet table, out of the constant cache:
+                                                                 // a per-lane index there would replay 32 ways
+    __shared__ __align__(16) uint8_t s_raw[K1_CHUNK + K1_MAXK + 24];
+    s_lut[threadIdx.x] = c_code_lut[threadIdx.x];
     // locate (operand, chunk) of this CTA
     int lo = 0, hi = n_ops;                 // last op with prefix <= blockIdx.x
     const int bid = blockIdx.x;
@@ -64,63 +94,98 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
     const int nload = min(K1_CHUNK + k - 1, op.len - base0);     // bases this CTA needs
     const bool upper = (op.flags & OPF_UPPER) != 0;
     const uint8_t* src = seq + op.seq_begin + base0;
+    __syncthreads();
 
-    for (int i = threadIdx.x; i < nload; i += K1_THREADS) {
-        uint8_t b = src[i];
-        if (upper && b >= 'a' && b <= 'z') b -= 32;              // str.upper() on ASCII
-        s_code[i] = c_code_lut[b];
+    // ---- bases -> codes: aligned 32-bit loads, four table look-ups, one 32-bit shared store ----------------
+    const int head = (int)(reinterpret_cast<uintptr_t>(src) & 3);    // s_code[i] = code of base i lives at s_raw[head + i]
+    {
+        const uint32_t* src4 = reinterpret_cast<const uint32_t*>(src - head);
+        const int nwords = (head + nload + 3) >> 2;
+        for (int j = threadIdx.x; j < nwords; j += K1_THREADS) {
+            uint32_t w = src4[j], c4 = 0;
+            #pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t b = (w >> (8 * e)) & 0xFFu;
+                if (upper && b >= 'a' && b <= 'z') b -= 32;          // str.upper() on ASCII
+                c4 |= (uint32_t)s_lut[b] << (8 * e);
+            }
+            reinterpret_cast<uint32_t*>(s_raw)[j] = c4;
+        }
     }
     __syncthreads();
+    const uint8_t* s_code = s_raw + head;
 
     const int npos_code = min(K1_CHUNK, op.len - base0);          // bases owned by this chunk
     const int npos_hash = min(K1_CHUNK, op.n - base0);            // k-mers owned by this chunk (may be <= 0)
     const bool is_read = (op.flags & OPF_READ) != 0;
     bool bad_read = false;
-
-    for (int i = threadIdx.x; i < npos_code; i += K1_THREADS) {
-        int c0 = s_code[i];
-        uint32_t h = H_STRUCT_INVALID;
-        bool pal = false;
-        if (i < npos_hash) {
-            bool invalid = false, pure = true;
-            #pragma unroll 1
+    const int p0 = threadIdx.x * K1_RUN;
+    if (p0 < npos_code) {
+        uint32_t words[K1_RUN];
+        uint8_t codes[K1_RUN];
+        // rolling state of the window [p, p+k): 2-bit forward / reverse-complement words (k <= 15), how many of its
+        // codes are not plain ACGT, how many are invalid
+        const bool exact_k = k <= 15;
+        const uint32_t mask = exact_k ? ((k == 16 ? 0u : (1u << (2 * k))) - 1u) : 0u;
+        uint32_t f = 0, r = 0;
+        int n_np = 0, n_inv = 0;
+        if (p0 < npos_hash) {
             for (int t = 0; t < k; ++t) {
-                int c = s_code[i + t];
-                invalid |= (c == CODE_INVALID);
-                pure &= (c < 4);
+                const int c = s_code[p0 + t];
+                n_np += (c >= 4); n_inv += (c == CODE_INVALID);
+                if (exact_k) {
+                    f = ((f << 2) | (uint32_t)(c & 3)) & mask;
+                    r = (r >> 2) | ((uint32_t)(3 - (c & 3)) << (2 * (k - 1)));
+                }
             }
-            if (invalid) {
-                if (is_read) { bad_read = true; h = H_READ_PAD; }
-            } else if (pure && k <= 15) {
-                uint32_t f = 0, r = 0;
-                #pragma unroll 1
-                for (int t = 0; t < k; ++t) {
-                    f = (f << 2) | (uint32_t)s_code[i + t];
-                    r = (r << 2) | (uint32_t)(3 - s_code[i + k - 1 - t]);
-                }
-                pal = (f == r);
-                h = mix30(min(f, r)) | (pal ? H_PALINDROME : 0u);
-            } else {
-                const uint64_t B = 0x9E3779B97F4A7C15ull | 1ull;
-                uint64_t f = 0, r = 0;
-                #pragma unroll 1
-                for (int t = 0; t < k; ++t) {
-                    f = f * B + (uint64_t)(s_code[i + t] + 1);
-                    r = r * B + (uint64_t)(comp_code(s_code[i + k - 1 - t]) + 1);
-                }
-                if (f == r) {                          // candidate palindrome: confirm exactly
-                    pal = true;
-                    for (int t = 0; t < k; ++t)
-                        pal &= (s_code[i + t] == comp_code(s_code[i + k - 1 - t]));
-                }
-                uint64_t cmin = f < r ? f : r, cmax = f < r ? r : f;
-                uint32_t h30 = (uint32_t)(fmix64(cmin ^ (cmax * 0xD6E8FEB86659FD93ull)) >> 34);
-                h = H_NEEDS_VERIFY | (pal ? H_PALINDROME : 0u) | h30;
-                if (h > H_MAX_VALID) h -= 4;
-            }
-            hash[op.hash_off + base0 + i] = h;
         }
-        code[op.code_off + base0 + i] = (uint8_t)(c0 | (pal ? 0x80 : 0));
+        #pragma unroll
+        for (int i = 0; i < K1_RUN; ++i) {
+            const int p = p0 + i;
+            const int c0 = (p < npos_code) ? s_code[p] : 0;
+            uint32_t h = H_STRUCT_INVALID;
+            bool pal = false;
+            if (p < npos_hash) {
+                if (n_inv > 0) {
+                    if (is_read) { bad_read = true; h = H_READ_PAD; }
+                } else if (exact_k && n_np == 0) {
+                    pal = (f == r);
+                    h = mix30(min(f, r)) | (pal ? H_PALINDROME : 0u);
+                } else {
+                    h = k1_hashed_word(s_code + p, k, pal);
+                }
+                if (p + 1 < npos_hash) {                           // roll the window one base on
+                    const int cn = s_code[p + k];
+                    n_np += (cn >= 4) - (c0 >= 4);
+                    n_inv += (cn == CODE_INVALID) - (c0 == CODE_INVALID);
+                    if (exact_k) {
+                        f = ((f << 2) | (uint32_t)(cn & 3)) & mask;
+                        r = (r >> 2) | ((uint32_t)(3 - (cn & 3)) << (2 * (k - 1)));
+                    }
+                }
+            }
+            words[i] = h;
+            codes[i] = (uint8_t)(c0 | (pal ? 0x80 : 0));
+        }
+        // ---- stores: 8 words = two 16-byte stores, 8 codes = one 8-byte store when the run is complete --------
+        uint32_t* hp = hash + op.hash_off + base0 + p0;
+        uint8_t* cp = code + op.code_off + base0 + p0;
+        if (p0 + K1_RUN <= npos_hash) {
+            reinterpret_cast<uint4*>(hp)[0] = make_uint4(words[0], words[1], words[2], words[3]);
+            reinterpret_cast<uint4*>(hp)[1] = make_uint4(words[4], words[5], words[6], words[7]);
+        } else {
+            #pragma unroll
+            for (int i = 0; i < K1_RUN; ++i) if (p0 + i < npos_hash) hp[i] = words[i];
+        }
+        if (p0 + K1_RUN <= npos_code) {
+            uint2 v;
+            v.x = codes[0] | (codes[1] << 8) | (codes[2] << 16) | ((uint32_t)codes[3] << 24);
+            v.y = codes[4] | (codes[5] << 8) | (codes[6] << 16) | ((uint32_t)codes[7] << 24);
+            *reinterpret_cast<uint2*>(cp) = v;
+        } else {
+            #pragma unroll
+            for (int i = 0; i < K1_RUN; ++i) if (p0 + i < npos_code) cp[i] = codes[i];
+        }
     }
     if (bad_read) atomicOr(&op_status[lo], 1);
 }
