@@ -25,25 +25,30 @@ namespace vb {
 
 constexpr int K3_THREADS = 256;
 
-// scratch layout in 32-bit words for a value range of NB
+// scratch layout in 32-bit words for a value range of NB: two group sets (y-x and y+x are clustered side by
+// side, so no flag has to travel through global memory between them) + one small histogram
 __host__ __device__ inline int k3_words_bitmap(int nb) { return (nb + 31) / 32 + 1; }
 __host__ __device__ inline int k3_words_groups(int nb) { return nb / 10 + 4; }
 __host__ __device__ inline size_t k3_scratch_words(int nb) {
-    return 3 * (size_t)k3_words_bitmap(nb) + 2 * (size_t)k3_words_groups(nb) + 8;
+    return 2 * (3 * (size_t)k3_words_bitmap(nb) + (size_t)k3_words_groups(nb)) + (size_t)k3_words_groups(nb) + 8;
 }
 
-struct K3Scratch {
+struct K3Groups {       // chain groups of one value axis
     uint32_t* present;  // bitmap of occupied values
     uint32_t* start;    // bitmap of group starts
     uint32_t* wpref;    // [W+1] exclusive prefix of popc(start[w])
     uint32_t* gsize;    // [ng]   dots in every group
+};
+
+struct K3Scratch {
+    K3Groups D, A;      // groups of y-x (diagonals) and of y+x (anti-diagonals)
     uint32_t* aux;      // [nb/10+4] small histogram (median of the modal sub-bin)
 };
 
 struct K3Shared {       // block-wide accumulators (static shared memory)
     unsigned long long u64a, u64b;
     long long s64;
-    unsigned int u32a, u32b, u32c, gmax;
+    unsigned int u32a, u32b, u32c, gmaxD, gmaxA;
     int imin, imax;
     int ng;
     unsigned int cnt11[11];
@@ -55,11 +60,14 @@ struct K3Shared {       // block-wide accumulators (static shared memory)
 
 __device__ __forceinline__ void k3_setup_scratch(K3Scratch& s, uint32_t* base, int nb_cap) {
     const int wb = k3_words_bitmap(nb_cap), wg = k3_words_groups(nb_cap);
-    s.present = base;
-    s.start = s.present + wb;
-    s.wpref = s.start + wb;
-    s.gsize = s.wpref + wb;
-    s.aux = s.gsize + wg;
+    K3Groups* sets[2] = {&s.D, &s.A};
+    for (int i = 0; i < 2; ++i) {
+        sets[i]->present = base; base += wb;
+        sets[i]->start = base;   base += wb;
+        sets[i]->wpref = base;   base += wb;
+        sets[i]->gsize = base;   base += wg;
+    }
+    s.aux = base;
 }
 
 // inclusive prefix sum of arr[0..N) in place; every thread of the block must call it
@@ -95,30 +103,25 @@ __device__ __forceinline__ void k3_warp_count_add(uint32_t* C, int idx) {
     if (idx >= 0 && lane == __ffs(peers) - 1) atomicAdd(&C[idx], (uint32_t)__popc(peers));
 }
 
-__device__ __forceinline__ int k3_group_of(const K3Scratch& s, int b) {
+__device__ __forceinline__ int k3_group_of(const K3Groups& s, int b) {
     const int w = b >> 5;
     return (int)s.wpref[w] + __popc(s.start[w] & (0xFFFFFFFFu >> (31 - (b & 31)))) - 1;
 }
+__device__ __forceinline__ uint32_t k3_group_size(const K3Groups& s, int b) {
+    return s.gsize[k3_group_of(s, b)];
+}
 
-// Chain groups of the values binf(hit) in [0, nb) over the hits of a plot (binf < 0 = hit not taken): runs of
-// occupied values whose gaps are < 10, and their sizes.  On return k3_group_size() answers per value, sh.ng is
-// the group count, sh.gmax the largest group.  Every thread of the block must call it.
-template <typename BinF>
-__device__ void k3_build_groups(const uint2* hits, uint32_t H, K3Scratch& s, int nb, K3Shared& sh, BinF binf) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int W = (nb + 31) >> 5;
-    for (int w = tid; w < W; w += K3_THREADS) s.present[w] = 0u;
-    if (tid == 0) { sh.gmax = 0; s.wpref[0] = 0; }
-    __syncthreads();
-    for (uint32_t i = tid; i < H; i += K3_THREADS) {
-        const int b = binf(hits[i]);
-        if (b >= 0) {
-            const uint32_t bit = 1u << (b & 31);
-            if (!(s.present[b >> 5] & bit)) atomicOr(&s.present[b >> 5], bit);      // most dots re-set a bit already set
-        }
-    }
-    __syncthreads();
-    for (int w = tid; w < W; w += K3_THREADS) {
+// steps of a clustering round on one group set (every thread of the block calls them; barriers are the caller's)
+__device__ __forceinline__ void k3_groups_clear(K3Groups& s, int W) {
+    for (int w = threadIdx.x; w < W; w += K3_THREADS) s.present[w] = 0u;
+    if (threadIdx.x == 0) s.wpref[0] = 0;
+}
+__device__ __forceinline__ void k3_groups_mark(K3Groups& s, int b) {
+    const uint32_t bit = 1u << (b & 31);
+    if (!(s.present[b >> 5] & bit)) atomicOr(&s.present[b >> 5], bit);      // most dots re-set a bit already set
+}
+__device__ __forceinline__ void k3_groups_starts(K3Groups& s, int W) {
+    for (int w = threadIdx.x; w < W; w += K3_THREADS) {
         const uint32_t cur = s.present[w], prev = w ? s.present[w - 1] : 0u;
         const unsigned long long comb = ((unsigned long long)cur << 32) | prev;
         unsigned long long near = 0;
@@ -128,11 +131,35 @@ __device__ void k3_build_groups(const uint2* hits, uint32_t H, K3Scratch& s, int
         s.start[w] = st;
         s.wpref[w + 1] = __popc(st);
     }
+}
+__device__ __forceinline__ uint32_t k3_groups_max(const K3Groups& s, int ng) {      // block-wide maximum via the caller's atomicMax
+    uint32_t lmax = 0;
+    for (int g = threadIdx.x; g < ng; g += K3_THREADS) lmax = max(lmax, s.gsize[g]);
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xFFFFFFFFu, lmax, o));
+    return lmax;
+}
+
+// Chain groups of the values binf(hit) in [0, nb) over the hits of a plot (binf < 0 = hit not taken): runs of
+// occupied values whose gaps are < 10, and their sizes.  On return k3_group_size(set, value) answers per value and
+// `gmax` (a field of sh) holds the largest group.  Every thread of the block must call it.
+template <typename BinF>
+__device__ void k3_build_groups(const uint2* hits, uint32_t H, K3Groups& s, int nb, K3Shared& sh, unsigned int K3Shared::*gmax, BinF binf) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int W = (nb + 31) >> 5;
+    k3_groups_clear(s, W);
+    if (tid == 0) sh.*gmax = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < H; i += K3_THREADS) {
+        const int b = binf(hits[i]);
+        if (b >= 0) k3_groups_mark(s, b);
+    }
+    __syncthreads();
+    k3_groups_starts(s, W);
     __syncthreads();
     k3_block_scan(s.wpref + 1, W, sh);
     const int ng = (int)s.wpref[W];
     for (int g = tid; g < ng; g += K3_THREADS) s.gsize[g] = 0u;
-    if (tid == 0) sh.ng = ng;
     __syncthreads();
     for (uint32_t base = 0; base < H; base += K3_THREADS) {            // uniform trip count: warp-aggregated adds
         const uint32_t i = base + tid;
@@ -141,16 +168,9 @@ __device__ void k3_build_groups(const uint2* hits, uint32_t H, K3Scratch& s, int
         k3_warp_count_add(s.gsize, g);
     }
     __syncthreads();
-    uint32_t lmax = 0;
-    for (int g = tid; g < ng; g += K3_THREADS) lmax = max(lmax, s.gsize[g]);
-    #pragma unroll
-    for (int o = 16; o; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xFFFFFFFFu, lmax, o));
-    if (lane == 0 && lmax) atomicMax(&sh.gmax, lmax);
+    const uint32_t lmax = k3_groups_max(s, ng);
+    if (lane == 0 && lmax) atomicMax(&(sh.*gmax), lmax);
     __syncthreads();
-}
-
-__device__ __forceinline__ uint32_t k3_group_size(const K3Scratch& s, int b) {
-    return s.gsize[k3_group_of(s, b)];
 }
 
 __device__ __forceinline__ void k3_zero(uint32_t* a, int n) {
@@ -196,29 +216,65 @@ __device__ void k3_pass0(const PlotView& v, K3Shared& sh, int& minx, int& maxx, 
     __syncthreads();
 }
 
-// clean_dotdata_diagnal_and_anti_diagnal (Simple_function.pyx:432-448): keep a dot unless its y-x
-// chain group and its y+x chain group both have <= 10 members.  Sets HIT_F_CLEAN; returns count and
-// sum |x-y| of the kept dots.
-__device__ void k3_clean_a6(const PlotView& v, K3Scratch& s, K3Shared& sh, PlotStat& st) {
-    const int nb = v.n + v.m - 1;
-    const int moff = v.m - 1;
-    k3_build_groups(v.hits, v.H, s, nb, sh, [moff](const uint2& h) { return (int)(h.y & HIT_Y_MASK) - (int)h.x + moff; });
-    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
-        uint2 h = v.hits[i];
-        const uint32_t y = h.y & HIT_Y_MASK;
-        const bool keep = k3_group_size(s, (int)y - (int)h.x + v.m - 1) > 10u;
-        v.hits[i].y = y | (keep ? HIT_F_KEEP1 : 0u);
+// Chain groups of y-x into set D and of y+x into set A in one go: every hit is read twice instead of four times,
+// and both sets stay available, so no flag has to be written back between the two clusterings.
+__device__ void k3_build_groups_both(const PlotView& v, K3Scratch& s, K3Shared& sh) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nb = v.n + v.m - 1, moff = v.m - 1;
+    const int W = (nb + 31) >> 5;
+    k3_groups_clear(s.D, W);
+    k3_groups_clear(s.A, W);
+    if (tid == 0) { sh.gmaxD = 0; sh.gmaxA = 0; }
+    __syncthreads();
+    for (uint32_t i = tid; i < v.H; i += K3_THREADS) {
+        const uint2 h = v.hits[i];
+        const int x = (int)h.x, y = (int)(h.y & HIT_Y_MASK);
+        k3_groups_mark(s.D, y - x + moff);
+        k3_groups_mark(s.A, y + x);
     }
+    __syncthreads();
+    k3_groups_starts(s.D, W);
+    k3_groups_starts(s.A, W);
+    __syncthreads();
+    k3_block_scan(s.D.wpref + 1, W, sh);
+    k3_block_scan(s.A.wpref + 1, W, sh);
+    const int ngD = (int)s.D.wpref[W], ngA = (int)s.A.wpref[W];
+    for (int g = tid; g < ngD; g += K3_THREADS) s.D.gsize[g] = 0u;
+    for (int g = tid; g < ngA; g += K3_THREADS) s.A.gsize[g] = 0u;
+    __syncthreads();
+    for (uint32_t base = 0; base < v.H; base += K3_THREADS) {          // uniform trip count: warp-aggregated adds
+        const uint32_t i = base + tid;
+        int gd = -1, ga = -1;
+        if (i < v.H) {
+            const uint2 h = v.hits[i];
+            const int x = (int)h.x, y = (int)(h.y & HIT_Y_MASK);
+            gd = k3_group_of(s.D, y - x + moff);
+            ga = k3_group_of(s.A, y + x);
+        }
+        k3_warp_count_add(s.D.gsize, gd);
+        k3_warp_count_add(s.A.gsize, ga);
+    }
+    __syncthreads();
+    const uint32_t mD = k3_groups_max(s.D, ngD), mA = k3_groups_max(s.A, ngA);
+    if (lane == 0) { if (mD) atomicMax(&sh.gmaxD, mD); if (mA) atomicMax(&sh.gmaxA, mA); }
+    __syncthreads();
+}
+
+// clean_dotdata_diagnal_and_anti_diagnal (Simple_function.pyx:432-448): keep a dot unless its y-x
+// chain group and its y+x chain group both have <= 10 members.  Returns count and sum |x-y| of the kept dots;
+// sets HIT_F_CLEAN on them when `write_flags` (the REDEF statistics read it back).
+__device__ void k3_clean_a6(const PlotView& v, K3Scratch& s, K3Shared& sh, PlotStat& st, bool write_flags) {
+    const int moff = v.m - 1;
+    k3_build_groups_both(v, s, sh);
     if (threadIdx.x == 0) { sh.u32a = 0; sh.u64a = 0; }
     __syncthreads();
-    k3_build_groups(v.hits, v.H, s, nb, sh, [](const uint2& h) { return (int)(h.y & HIT_Y_MASK) + (int)h.x; });
     uint32_t lcnt = 0; unsigned long long lsum = 0;
     for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
-        uint2 h = v.hits[i];
-        const uint32_t y = h.y & HIT_Y_MASK;
-        const bool keep = (h.y & HIT_F_KEEP1) || k3_group_size(s, (int)y + (int)h.x) > 10u;
-        v.hits[i].y = y | (keep ? HIT_F_CLEAN : 0u);
-        if (keep) { ++lcnt; lsum += (unsigned long long)abs((int)h.x - (int)y); }
+        const uint2 h = v.hits[i];
+        const int x = (int)h.x, y = (int)(h.y & HIT_Y_MASK);
+        const bool keep = k3_group_size(s.D, y - x + moff) > 10u || k3_group_size(s.A, y + x) > 10u;
+        if (write_flags) v.hits[i].y = (uint32_t)y | (keep ? HIT_F_CLEAN : 0u);
+        if (keep) { ++lcnt; lsum += (unsigned long long)abs(x - y); }
     }
     #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -243,37 +299,35 @@ __device__ void k3_clean_w10(const PlotView& v, K3Scratch& s, K3Shared& sh, Plot
     st.nclean = 0; st.cnt10 = 0;
     if (v.H == 0) return;                               // uniform across the block
     const int nb = v.n + v.m - 1;
-    if (threadIdx.x == 0) { sh.u32a = 0; sh.u32b = 0; sh.u32c = 0; }
     const int moff = v.m - 1;
-    k3_build_groups(v.hits, v.H, s, nb, sh, [moff](const uint2& h) { return (int)(h.y & HIT_Y_MASK) - (int)h.x + moff; });
-    const uint32_t gmax1 = sh.gmax;
+    if (threadIdx.x == 0) { sh.u32a = 0; sh.u32b = 0; sh.u32c = 0; }
+    k3_build_groups(v.hits, v.H, s.D, nb, sh, &K3Shared::gmaxD,
+                    [moff](const uint2& h) { return (int)(h.y & HIT_Y_MASK) - (int)h.x + moff; });
+    const uint32_t gmax1 = sh.gmaxD;
+    const K3Groups D = s.D;
+    auto kept1 = [D, moff, gmax1](const uint2& h) {
+        return k3_a7_keep(k3_group_size(D, (int)(h.y & HIT_Y_MASK) - (int)h.x + moff), gmax1);
+    };
     uint32_t lkept = 0;
-    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
-        uint2 h = v.hits[i];
-        const uint32_t y = h.y & HIT_Y_MASK;
-        const bool keep = k3_a7_keep(k3_group_size(s, (int)y - (int)h.x + v.m - 1), gmax1);
-        v.hits[i].y = y | (keep ? HIT_F_KEEP1 : 0u);
-        lkept += keep;
-    }
+    for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) lkept += kept1(v.hits[i]);
     #pragma unroll
     for (int o = 16; o; o >>= 1) lkept += __shfl_xor_sync(0xFFFFFFFFu, lkept, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(&sh.u32a, lkept);
     __syncthreads();
-    const uint32_t kept1 = sh.u32a;
-    const bool have_left = kept1 < v.H;
+    const uint32_t kept1_n = sh.u32a;
+    const bool have_left = kept1_n < v.H;
     uint32_t gmax2 = 0;
-    if (have_left) {
-        k3_build_groups(v.hits, v.H, s, nb, sh,
-                        [](const uint2& h) { return (h.y & HIT_F_KEEP1) ? -1 : (int)(h.y & HIT_Y_MASK) + (int)h.x; });
-        gmax2 = sh.gmax;
+    if (have_left) {                                     // second clustering, on y+x, over the dots the first did not keep
+        k3_build_groups(v.hits, v.H, s.A, nb, sh, &K3Shared::gmaxA,
+                        [kept1](const uint2& h) { return kept1(h) ? -1 : (int)(h.y & HIT_Y_MASK) + (int)h.x; });
+        gmax2 = sh.gmaxA;
     }
     uint32_t lcnt = 0, l10 = 0;
     for (uint32_t i = threadIdx.x; i < v.H; i += K3_THREADS) {
-        uint2 h = v.hits[i];
+        const uint2 h = v.hits[i];
         const uint32_t y = h.y & HIT_Y_MASK;
-        bool keep = (h.y & HIT_F_KEEP1) != 0;
-        if (!keep && have_left) keep = k3_a7_keep(k3_group_size(s, (int)y + (int)h.x), gmax2);
-        v.hits[i].y = y | (keep ? HIT_F_CLEAN : 0u);
+        bool keep = kept1(h);
+        if (!keep && have_left) keep = k3_a7_keep(k3_group_size(s.A, (int)y + (int)h.x), gmax2);
         if (keep) {
             ++lcnt;
             const int x = (int)h.x;
@@ -470,8 +524,8 @@ __device__ void k3_eval(int mode, const PlotView& pr, const PlotView& pa, int le
         const bool rs = (double)(rmaxx - rminx) / Lr > 0.6;
         const bool as = (double)(amaxx - aminx) / La > 0.6;
         if (rs && as) {
-            k3_clean_a6(pr, s, sh, sr);
-            k3_clean_a6(pa, s, sh, sa);
+            k3_clean_a6(pr, s, sh, sr, false);
+            k3_clean_a6(pa, s, sh, sa, false);
             if (sr.nclean > 0 && sa.nclean > 0) {
                 out.a = (double)sr.sumabs / (double)sr.nclean;      // np.mean of exact integers
                 out.b = (double)sa.sumabs / (double)sa.nclean;
@@ -486,8 +540,8 @@ __device__ void k3_eval(int mode, const PlotView& pr, const PlotView& pa, int le
     } else {                                           // REDEF, Simple_function.pyx:244-257
         if (!(Hr / Lr > 0.1 && Ha / La > 0.1)) return;
         if (!((double)(rmaxx - rminx) / Lr > 0.7 && (double)(amaxx - aminx) / La > 0.7)) return;
-        k3_clean_a6(pr, s, sh, sr);
-        k3_clean_a6(pa, s, sh, sa);
+        k3_clean_a6(pr, s, sh, sr, true);
+        k3_clean_a6(pa, s, sh, sa, true);
         if (sr.nclean > 0 && sa.nclean > 0) {
             k3_redef_stat(pr, s, sh, sr);
             k3_redef_stat(pa, s, sh, sa);
