@@ -184,6 +184,24 @@ __device__ __forceinline__ void k2_flush(const K2Strip& st, const uint2* queue, 
     }
 }
 
+// Park matched cells in the per-warp hit queue (about 1e-4 of all cells get here): `hm` = rows j of this lane's
+// note equal to the streamed word `ve` at coordinate `cs`; row j sits at coordinate `cr0 + 32 j`.  Slots by ballot +
+// popc; the queue is emitted when it cannot take another round.  Warp-collective.
+__device__ __forceinline__ void k2_park(uint32_t hm, uint32_t ve, int cs, int cr0, const K2Strip& st, uint2* queue, int& qn, int lane)
+{
+    while (true) {
+        const unsigned act = __ballot_sync(0xFFFFFFFFu, hm != 0u);
+        if (act == 0u) break;
+        if (qn + __popc(act) > K2_QCAP) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
+        if (hm) {
+            const int j = __ffs(hm) - 1;
+            hm &= hm - 1;
+            queue[qn + __popc(act & ((1u << lane) - 1u))] = make_uint2((uint32_t)cs | (ve & 0xC0000000u), (uint32_t)(cr0 + 32 * j));
+        }
+        qn += __popc(act);
+    }
+}
+
 // Resolve candidate notes, one note per lane and round: the 8 rows of the noted lane's group (fetched by shuffle:
 // every lane names its own source lane) against the 32 streamed words of the noted block.  Lanes walk the block in
 // rotated order so the shared-memory reads of a round never share a bank.  Matches are parked in the hit queue.
@@ -209,38 +227,42 @@ __device__ __forceinline__ void k2_resolve(const uint32_t (&r)[R], const uint32_
         }
         const int gbase = g == 0 ? G::base(0) : (g == 1 ? G::base(1) : (g == 2 ? G::base(2) : G::base(3)));
         const uint32_t* sblk = sb + b * 32;
-        #pragma unroll 1
-        for (int t0 = 0; t0 < 32; t0 += 8) {                        // 8 streamed words per step: loads and compares overlap
-            uint32_t v[8];
-            #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = sblk[(t0 + e + lane) & 31];
+        // pass 1, no warp-collective work: every lane walks its block and remembers (up to 4) positions whose word
+        // equals one of its 8 rows; predicated bookkeeping only, so the loop runs at full rate
+        uint32_t rec = 0, cnt = 0;
+        #pragma unroll 4
+        for (int t = 0; t < 32; ++t) {
+            const int tt = (t + lane) & 31;
+            const uint32_t v = sblk[tt];
             bool any = false;
             #pragma unroll
-            for (int e = 0; e < 8; ++e)
-                #pragma unroll
-                for (int j = 0; j < K2_D; ++j) any |= (rows[j] == v[e]);
-            if (__ballot_sync(0xFFFFFFFFu, any) == 0u) continue;
-            #pragma unroll 1
-            for (int e = 0; e < 8; ++e) {                           // a match somewhere in these 8 x 8 x 32 cells: find it
-                const int tt = (t0 + e + lane) & 31;
-                const uint32_t ve = sblk[tt];
-                uint32_t hm = 0;
+            for (int j = 0; j < K2_D; ++j) any |= (v == rows[j]);
+            if (any) { rec = (rec << 8) | (uint32_t)tt; ++cnt; }
+        }
+        // pass 2: the remembered positions, one per lane and step (a note has one dot in the typical case)
+        const unsigned many = __ballot_sync(0xFFFFFFFFu, cnt > 4u);     // repeats: more matches than rec holds
+        for (uint32_t step = 0; step < 4; ++step) {
+            const bool mine = step < min(cnt, 4u);
+            if (__ballot_sync(0xFFFFFFFFu, mine) == 0u) break;
+            const int tt = (int)((rec >> (8 * step)) & 31u);
+            const uint32_t ve = sblk[tt];
+            uint32_t hm = 0;
+            if (mine && !((many >> lane) & 1u)) {
                 #pragma unroll
                 for (int j = 0; j < K2_D; ++j) if (rows[j] == ve) hm |= 1u << j;
-                // park the matched cells (about 1e-4 of all cells): slots by ballot + popc
-                while (true) {
-                    const unsigned act = __ballot_sync(0xFFFFFFFFu, hm != 0u);
-                    if (act == 0u) break;
-                    if (qn + __popc(act) > K2_QCAP) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
-                    if (hm) {
-                        const int j = __ffs(hm) - 1;
-                        hm &= hm - 1;
-                        const uint32_t cs_ = (uint32_t)(stream_origin + b * 32 + tt);        // coordinate on the streamed axis
-                        const uint32_t cr_ = (uint32_t)(row0 + (gbase + j) * 32 + L);         // coordinate on the row axis
-                        queue[qn + __popc(act & ((1u << lane) - 1u))] = make_uint2(cs_ | (ve & 0xC0000000u), cr_);
-                    }
-                    qn += __popc(act);
+            }
+            k2_park(hm, ve, stream_origin + b * 32 + tt, row0 + gbase * 32 + L, st, queue, qn, lane);
+        }
+        if (many) {                                                 // rare: walk the block again, parking as we go
+            for (int t = 0; t < 32; ++t) {
+                const int tt = (t + lane) & 31;
+                const uint32_t ve = sblk[tt];
+                uint32_t hm = 0;
+                if ((many >> lane) & 1u) {
+                    #pragma unroll
+                    for (int j = 0; j < K2_D; ++j) if (rows[j] == ve) hm |= 1u << j;
                 }
+                k2_park(hm, ve, stream_origin + b * 32 + tt, row0 + gbase * 32 + L, st, queue, qn, lane);
             }
         }
     }
