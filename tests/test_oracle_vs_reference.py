@@ -89,3 +89,22 @@ try:
         assert np.array_equal(d1, O.dotdata(k, read, struct))
 except ImportError:      # pragma: no cover
     pass
+
+
+def test_dotdata_property_small_alphabet_strings():
+    """hypothesis: on short strings over ACGT + N + lower case + IUPAC (palindromic k-mers, repeats and N runs are
+    frequent at this size) the oracle's dotdata equals the reference's, row for row, for every k the reference uses
+    and a few it does not."""
+    from hypothesis import given, settings, strategies as st_
+
+    alphabet = st_.sampled_from(list("ACGTACGTACGTNacgtRYn"))
+
+    @settings(max_examples=120, deadline=None)
+    @given(read=st_.text(alphabet, min_size=0, max_size=70), struct=st_.text(alphabet, min_size=0, max_size=90),
+           k=st_.sampled_from([2, 4, 6, 10, 20]))
+    def check(read, struct, k):
+        exp = [tuple(x) for x in R.dotdata(k, read, struct)]
+        got = [tuple(x) for x in O.dotdata(k, read, struct).tolist()]
+        assert got == exp
+
+    check()
