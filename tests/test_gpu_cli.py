@@ -97,3 +97,18 @@ def test_worker_processes_same_output(tmp_path):
         outs.append(open(out).read())
     assert outs[0] == outs[1]
     CC.compare_bed_tables(os.path.join(str(tmp_path), "bed_p2.vapor"), os.path.join(CC.CASE, "svs.bed.vapor.golden"))
+
+
+def test_figure_hook_writes_dot_lists(tmp_path, session, monkeypatch):
+    """VAPOR_FIGURES=tsv: the four recurrence plots the reference draws per event (ref/ref, alt/alt, best read/ref,
+    best read/alt; Simple_function.pyx:1072-1089) are written as dot lists computed on the GPU."""
+    monkeypatch.setenv("VAPOR_FIGURES", "tsv")
+    fig = os.path.join(str(tmp_path), "ev.png")
+    scores = SF.vapor_simple_inv_Vapor(3, 1, os.path.join(CC.CASE, "reads.sam.gz"), os.path.join(CC.CASE, "ref.fa"),
+                                       ["chr1", 24714, 25480], fig)
+    assert len(scores) > 3
+    rows = [l.split("\t") for l in open(fig + ".dots.tsv")]
+    names = {r[0] for r in rows}
+    assert names == {"ref_vs_ref", "alt_vs_alt", "read_vs_ref", "read_vs_alt"}
+    diag = [r for r in rows if r[0] == "ref_vs_ref" and r[1] == r[2].strip()]
+    assert len(diag) > 1000                                   # the self-plot holds the whole diagonal

@@ -353,6 +353,16 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
         for (size_t wi = 0; wi < h->waves.size(); ++wi)
             for (int64_t t = h->waves[wi].task_begin; t < h->waves[wi].task_end; ++t)
                 h->class_ids[cur[wi * K3_NCLASS + cls[t]]++] = (int32_t)t;
+        // longest tasks first inside every launch (cost ~ rows + columns of the task's plots): short tasks fill the tail
+        std::vector<int32_t> cost(n_task);
+        for (int64_t t = 0; t < n_task; ++t) {
+            int c = 0;
+            for (int i = 0; i < 4; ++i) if (h->tasks[t].plot[i] >= 0) { const Plot& p = h->plots[h->tasks[t].plot[i]]; c += p.n + p.m; }
+            cost[t] = c;
+        }
+        for (size_t g = 0; g + 1 < h->class_off.size(); ++g)
+            std::stable_sort(h->class_ids.begin() + h->class_off[g], h->class_ids.begin() + h->class_off[g + 1],
+                             [&](int32_t a, int32_t b) { return cost[a] > cost[b]; });
     }
     h->n_task = n_task; h->n_sv = n_sv; h->n_seq = n_seq;
     h->seq_total = n_seq > 0 ? in->seq_off[n_seq] : 0;
