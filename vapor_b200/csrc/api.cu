@@ -48,22 +48,6 @@ struct DevBuf {                      // grow-only device buffer
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-template <typename T>
-struct PinBuf {                      // grow-only pinned host staging buffer
-    T* p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 8 + 64;
-        cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
 struct Wave {
     int64_t task_begin, task_end;
     int64_t plot_begin, plot_end;
@@ -106,15 +90,12 @@ struct Handle {
     DevBuf<Operand> d_ops;
     DevBuf<Plot> d_plots;
     DevBuf<Task> d_tasks;
-    DevBuf<int32_t> d_chunk_prefix, d_op_status, d_class_ids, d_sv_nscore, d_ovf_ids;
+    DevBuf<int32_t> d_chunk_prefix, d_op_status, d_class_ids, d_sv_nscore;
     DevBuf<int64_t> d_strip_prefix, d_sv_off, d_ovf_prefix;
     DevBuf<uint32_t> d_hash, d_cnt, d_task_hits, d_gscratch, d_misc, d_qc;
     DevBuf<uint2> d_hits, d_ovf_hits;
     DevBuf<double> d_task_score, d_task_stat, d_pos, d_sv_qs, d_sv_gs, d_sv_gq;
     DevBuf<unsigned long long> d_task_hitsum, d_queue;
-    // pinned staging
-    PinBuf<uint8_t> p_seq;
-    PinBuf<uint32_t> p_misc;
 
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     size_t ev_used = 0;
@@ -804,13 +785,12 @@ int vapor_gpu_close(void* handle) {
     cudaStreamSynchronize(h->stream);
     h->d_seq.release(); h->d_code.release(); h->d_task_status.release(); h->d_sv_gt.release();
     h->d_ops.release(); h->d_plots.release(); h->d_tasks.release();
-    h->d_chunk_prefix.release(); h->d_op_status.release(); h->d_class_ids.release(); h->d_sv_nscore.release(); h->d_ovf_ids.release();
+    h->d_chunk_prefix.release(); h->d_op_status.release(); h->d_class_ids.release(); h->d_sv_nscore.release();
     h->d_strip_prefix.release(); h->d_sv_off.release(); h->d_ovf_prefix.release();
     h->d_hash.release(); h->d_cnt.release(); h->d_task_hits.release(); h->d_gscratch.release(); h->d_misc.release(); h->d_qc.release();
     h->d_hits.release(); h->d_ovf_hits.release();
     h->d_task_score.release(); h->d_task_stat.release(); h->d_pos.release(); h->d_sv_qs.release(); h->d_sv_gs.release(); h->d_sv_gq.release();
     h->d_task_hitsum.release(); h->d_queue.release();
-    h->p_seq.release(); h->p_misc.release();
     for (auto& ev : h->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaStreamDestroy(h->stream);
     delete h;

@@ -59,9 +59,8 @@ struct Task {              // one read of one SV/allele
     int32_t mode;
 };
 
-// hits carry two flag bits in y while kernel 3 works on them
+// hits carry a flag bit in y while kernel 3 works on them (REDEF statistics)
 constexpr uint32_t HIT_Y_MASK   = 0x0FFFFFFFu;
-constexpr uint32_t HIT_F_KEEP1  = 0x40000000u;  // kept by the first (diagonal) clustering
 constexpr uint32_t HIT_F_CLEAN  = 0x80000000u;  // member of the cleaned dot set
 
 __host__ __device__ __forceinline__ uint64_t hit_mix(uint32_t x, uint32_t y) {
