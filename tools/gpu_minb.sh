@@ -1,4 +1,4 @@
-for mb in 4 5 6; do
+for mb in 5 6 4; do
   VAPOR_NVCC_EXTRA="-DK2_MINB=$mb" python -c "from vapor_b200 import _build; _build.build_native(force=True)"
   python bench.py --n-sv 2000 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_mb$mb.json 2> gpurun_out/bench_mb$mb.err
   python - <<PY

@@ -222,6 +222,59 @@ __global__ void __launch_bounds__(128) k_horner_a(const uint32_t* in, uint32_t* 
     if (found) out[0] = found;
 }
 
+// ---- V5: NH packed half2 registers (2*NH rows, 16-bit filters) through HSET2 + 3-input LOP3 on the alu pipe
+//           + NP degree-D row polynomials by Horner on the fma pipe; streamed word first in every instruction ----
+template <int NH, int NP, int D>
+__global__ void __launch_bounds__(128) k_hset2_horner(const uint32_t* in, uint32_t* out, int reps) {
+    __shared__ __align__(16) uint32_t s[4][TS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = lane; i < TS; i += 32) s[warp][i] = (in[(i * 7 + warp) & 4095] & 0xFFFFBBFFu) | 1u;
+    uint32_t h[NH], c[NP][D];
+    #pragma unroll
+    for (int q = 0; q < NH; ++q) h[q] = (in[(threadIdx.x * NH + q + blockIdx.x) & 4095] & 0x3BFE3BFEu) | 0x40004000u;
+    #pragma unroll
+    for (int p = 0; p < NP; ++p)
+        #pragma unroll
+        for (int q = 0; q < D; ++q) c[p][q] = in[(threadIdx.x * 16 + p * D + q + 5 * blockIdx.x) & 4095] | 1u;
+    __syncwarp();
+    uint32_t found = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+        for (int b = 0; b < TS / 32; ++b) {
+            const uint32_t* sblk = s[warp] + b * 32;
+            uint32_t a0 = 0xFFFFFFFFu, a1 = 0xFFFFFFFFu;
+            bool p2 = false, p3 = false;
+            #pragma unroll
+            for (int jj = 0; jj < 32; jj += 4) {
+                const uint4 v4 = *reinterpret_cast<const uint4*>(sblk + jj);
+                const uint32_t vw[4] = {v4.x, v4.y, v4.z, v4.w};
+                #pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t v = vw[e];
+                    const uint32_t vd = dup_lo(v);
+                    uint32_t acc[NP];
+                    #pragma unroll
+                    for (int p = 0; p < NP; ++p) acc[p] = v + c[p][0];
+                    #pragma unroll
+                    for (int q = 1; q < D; ++q)
+                        #pragma unroll
+                        for (int p = 0; p < NP; ++p) acc[p] = v * acc[p] + c[p][q];
+                    #pragma unroll
+                    for (int q = 0; q + 1 < NH; q += 2) {
+                        if ((q >> 1) & 1) a1 = and3(hne2(vd, h[q]), hne2(vd, h[q + 1]), a1);
+                        else              a0 = and3(hne2(vd, h[q]), hne2(vd, h[q + 1]), a0);
+                    }
+                    if (NH & 1) a0 &= hne2(vd, h[NH - 1]);
+                    #pragma unroll
+                    for (int p = 0; p < NP; ++p) { if (p & 1) p3 |= (acc[p] == 0); else p2 |= (acc[p] == 0); }
+                }
+            }
+            unsigned mask = __ballot_sync(0xFFFFFFFFu, ((a0 & a1) != 0xFFFFFFFFu) | p2 | p3);
+            if (mask) found += __popc(mask);
+        }
+    }
+    if (found) out[0] = found;
+}
+
 template <typename K>
 void run(const char* name, K kern, const uint32_t* in, uint32_t* out, double rows, int sm, int ctas_per_sm) {
     const int grid = sm * ctas_per_sm, reps = 64;
@@ -249,7 +302,7 @@ int main() {
     uint32_t x = 12345;
     for (int i = 0; i < 4096; ++i) { x = x * 1664525u + 1013904223u; h[i] = (x >> 2) & 0x3FFFFFFFu; }
     uint32_t *in, *out; cudaMalloc(&in, sizeof(h)); cudaMalloc(&out, 64); cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
-    for (int c : {4, 5}) {
+    for (int c : {4}) {
         run("isetp R=16", k_isetp<16>, in, out, 16, sm, c);
         run("isetp R=32", k_isetp<32>, in, out, 32, sm, c);
         run("hset2 NH=8  (16 rows)", k_hset2<8>, in, out, 16, sm, c);
@@ -263,6 +316,11 @@ int main() {
         run("horner NI=12 + 2 x deg 9 (30 rows)", k_horner<12, 2, 9>, in, out, 30, sm, c);
         run("horner NI=20 + 3 x deg 8 (44 rows)", k_horner<20, 3, 8>, in, out, 44, sm, c);
         run("horner-A NI=14 + 2 x deg 8 (30 rows)", k_horner_a<14, 2, 8>, in, out, 30, sm, c);
+        run("horner-A NI=13 + 2 x deg 8 (29 rows)", k_horner_a<13, 2, 8>, in, out, 29, sm, c);
+        run("hset2 NH=8 + 2 x deg 8 (32 rows)", k_hset2_horner<8, 2, 8>, in, out, 32, sm, c);
+        run("hset2 NH=9 + 2 x deg 8 (34 rows)", k_hset2_horner<9, 2, 8>, in, out, 34, sm, c);
+        run("hset2 NH=10 + 2 x deg 8 (36 rows)", k_hset2_horner<10, 2, 8>, in, out, 36, sm, c);
+        run("hset2 NH=12 + 3 x deg 8 (48 rows)", k_hset2_horner<12, 3, 8>, in, out, 48, sm, c);
         run("horner-A NI=16 + 2 x deg 8 (32 rows)", k_horner_a<16, 2, 8>, in, out, 32, sm, c);
         run("horner-A NI=12 + 2 x deg 8 (28 rows)", k_horner_a<12, 2, 8>, in, out, 28, sm, c);
         run("horner-A NI=20 + 3 x deg 8 (44 rows)", k_horner_a<20, 3, 8>, in, out, 44, sm, c);
