@@ -507,45 +507,53 @@ struct K3Params {
 };
 
 // One evaluation of one reference mode on the (ref, alt) plots.  Block-uniform control flow.
-__device__ void k3_eval(int mode, const PlotView& pr, const PlotView& pa, int len_ref, int len_alt,
-                        K3Scratch& s, K3Shared& sh, EvalResult& out,
-                        unsigned long long& csr, unsigned long long& csa)
+// Every phase below runs in a two-trip loop over (ref plot, alt plot) that is deliberately NOT unrolled, and the
+// kernel calls this function from one call site: fully inlined and unrolled the kernel was 318 KB of code and spent
+// more time waiting for instruction fetch than for anything else.
+__device__ void k3_eval(int mode, const PlotView* pv /*[2]: ref, alt*/, int len_ref, int len_alt,
+                        K3Scratch& s, K3Shared& sh, EvalResult& out, unsigned long long* cs /*[2]*/)
 {
-    int rminx, rmaxx, aminx, amaxx;
-    k3_pass0(pr, sh, rminx, rmaxx, csr);
-    k3_pass0(pa, sh, aminx, amaxx, csa);
+    int minx[2], maxx[2];
+    #pragma unroll 1
+    for (int w = 0; w < 2; ++w) k3_pass0(pv[w], sh, minx[w], maxx[w], cs[w]);
     out.a = 0; out.b = 0; out.valid = false;
-    const double Hr = (double)pr.H, Ha = (double)pa.H;
+    const double Hr = (double)pv[0].H, Ha = (double)pv[1].H;
     const double Lr = (double)len_ref, La = (double)len_alt;
-    PlotStat sr{}, sa{};
+    const double span_r = (double)(maxx[0] - minx[0]) / Lr, span_a = (double)(maxx[1] - minx[1]) / La;
+    PlotStat st[2] = {};
+    bool clean_a6 = false, clean_w10 = false;
     if (mode == 0) {                                   // ABS, Simple_function.pyx:187-203
-        if (!(pr.H > 2 && pa.H > 2)) return;
+        if (!(pv[0].H > 2 && pv[1].H > 2)) return;
         if (!(Hr / fmin(Lr, La) > 0.1)) return;
-        const bool rs = (double)(rmaxx - rminx) / Lr > 0.6;
-        const bool as = (double)(amaxx - aminx) / La > 0.6;
-        if (rs && as) {
-            k3_clean_a6(pr, s, sh, sr, false);
-            k3_clean_a6(pa, s, sh, sa, false);
-            if (sr.nclean > 0 && sa.nclean > 0) {
-                out.a = (double)sr.sumabs / (double)sr.nclean;      // np.mean of exact integers
-                out.b = (double)sa.sumabs / (double)sa.nclean;
-            }
-        } else if (rs) { out.a = 1.1; out.b = 2.1; }
-        else if (as)   { out.a = 2.1; out.b = 1.1; }
+        const bool rs = span_r > 0.6, as = span_a > 0.6;
+        if (rs && as) clean_a6 = true;
+        else if (rs) { out.a = 1.1; out.b = 2.1; }
+        else if (as) { out.a = 2.1; out.b = 1.1; }
     } else if (mode == 1) {                            // W10, Simple_function.pyx:280-294
         if (!(fmax(Hr / Lr, Ha / La) > 0.1)) return;
-        k3_clean_w10(pr, s, sh, sr);
-        k3_clean_w10(pa, s, sh, sa);
-        if (sr.nclean > 0 && sa.nclean > 0) { out.a = (double)sa.cnt10; out.b = (double)sr.cnt10; }   // swapped on purpose (:290)
+        clean_w10 = true;
     } else {                                           // REDEF, Simple_function.pyx:244-257
         if (!(Hr / Lr > 0.1 && Ha / La > 0.1)) return;
-        if (!((double)(rmaxx - rminx) / Lr > 0.7 && (double)(amaxx - aminx) / La > 0.7)) return;
-        k3_clean_a6(pr, s, sh, sr, true);
-        k3_clean_a6(pa, s, sh, sa, true);
-        if (sr.nclean > 0 && sa.nclean > 0) {
-            k3_redef_stat(pr, s, sh, sr);
-            k3_redef_stat(pa, s, sh, sa);
-            out.a = sr.dir; out.b = sa.dir;
+        if (!(span_r > 0.7 && span_a > 0.7)) return;
+        clean_a6 = true;
+    }
+    if (clean_a6) {
+        #pragma unroll 1
+        for (int w = 0; w < 2; ++w) k3_clean_a6(pv[w], s, sh, st[w], mode == 2);
+    } else if (clean_w10) {
+        #pragma unroll 1
+        for (int w = 0; w < 2; ++w) k3_clean_w10(pv[w], s, sh, st[w]);
+    }
+    if ((clean_a6 || clean_w10) && st[0].nclean > 0 && st[1].nclean > 0) {
+        if (mode == 0) {
+            out.a = (double)st[0].sumabs / (double)st[0].nclean;      // np.mean of exact integers
+            out.b = (double)st[1].sumabs / (double)st[1].nclean;
+        } else if (mode == 1) {
+            out.a = (double)st[1].cnt10; out.b = (double)st[0].cnt10;  // swapped on purpose (:290)
+        } else {
+            #pragma unroll 1
+            for (int w = 0; w < 2; ++w) k3_redef_stat(pv[w], s, sh, st[w]);
+            out.a = st[0].dir; out.b = st[1].dir;
         }
     }
     out.valid = (out.a != 0.0) && (out.b != 0.0);       // `if not 0 in pair`
@@ -571,13 +579,15 @@ k3_score_reads(const K3Params p)
             } else { pv[i].hits = nullptr; pv[i].H = 0; pv[i].n = 0; pv[i].m = 0; }
         }
         const bool bad = p.op_status[t.read_op] != 0;
-        EvalResult ea{0, 0, false}, eb{0, 0, false};
+        EvalResult ev[2] = {{0, 0, false}, {0, 0, false}};
         unsigned long long cs[4] = {0, 0, 0, 0};
         if (!bad) {
-            const int modeA = (t.mode == 3) ? 0 : t.mode;
-            k3_eval(modeA, pv[0], pv[1], t.len_ref, t.len_alt, s, sh, ea, cs[0], cs[1]);
-            if (t.mode == 3) k3_eval(1, pv[2], pv[3], t.len_ref, t.len_alt, s, sh, eb, cs[2], cs[3]);
+            const int n_eval = (t.mode == 3) ? 2 : 1;                   // the simple-DEL rule asks ABS, then W10
+            #pragma unroll 1
+            for (int e = 0; e < n_eval; ++e)
+                k3_eval((t.mode == 3) ? e : t.mode, pv + 2 * e, t.len_ref, t.len_alt, s, sh, ev[e], cs + 2 * e);
         }
+        const EvalResult ea = ev[0], eb = ev[1];
         if (threadIdx.x == 0) {
             double score = 0.0; uint8_t status = 0;
             if (bad) status = 2;
