@@ -67,16 +67,20 @@ def compare_annotated_vcf(got_path, exp_path):
                 assert gi[k] == ei[k], (k, gi[k], ei[k])
 
 
-def run_bed_case(tmp_path, session):
+CASE_LARGE = os.path.join(HERE, "golden", "cli_case_large")
+
+
+def run_bed_case(tmp_path, session, case=None):
+    case = case or CASE
     out = os.path.join(str(tmp_path), "bed.vapor")
-    args = Args(sv_input=os.path.join(CASE, "svs.bed"), output_path=os.path.join(str(tmp_path), "figs"), output_file=out,
-                reference=os.path.join(CASE, "ref.fa"), pacbio_input=os.path.join(CASE, "reads.sam.gz"))
+    args = Args(sv_input=os.path.join(case, "svs.bed"), output_path=os.path.join(str(tmp_path), "figs"), output_file=out,
+                reference=os.path.join(case, "ref.fa"), pacbio_input=os.path.join(case, "reads.sam.gz"))
     SF.set_session(session)
     try:
         cli.run_bed(args, [session])
     finally:
         SF.set_session(None)
-    compare_bed_tables(out, os.path.join(CASE, "svs.bed.vapor.golden"))
+    compare_bed_tables(out, os.path.join(case, "svs.bed.vapor.golden"))
 
 
 def run_vcf_case(tmp_path, session):

@@ -123,6 +123,55 @@ def main():
         shutil.rmtree(tmp, ignore_errors=True)
     for f in sorted(os.listdir(CASE)):
         print(f, os.path.getsize(os.path.join(CASE, f)))
+    make_large_case()
+
+
+def make_large_case():
+    """Second case, bed only: events of 10-12 kb (the drivers switch to 1 kb junction windows at >= 10 kb,
+    Simple_function.pyx:1728-1744, 1769-1783, 1918-1932) and a 5.5 kb insertion (short reference window, :1870-1871)."""
+    from vapor_b200 import synth_genome
+    case = os.path.join(HERE, "cli_case_large")
+    if os.path.isdir(case):
+        shutil.rmtree(case)
+    ds = synth_genome.make_dataset(case, seed=20261018 + 4, n_simple=4, n_complex=0, size_range=(10050, 11500), coverage=10.0,
+                                   read_len_mean=5000.0, ins_len_override=5500)
+    with open(ds.sam, "rb") as f, gzip.GzipFile(ds.sam + ".gz", "wb", mtime=0) as g:
+        shutil.copyfileobj(f, g)
+    os.remove(ds.sam)
+    os.remove(ds.vcf)
+    sam = ds.sam + ".gz"
+    tmp = tempfile.mkdtemp(prefix="vapor_ref_cli_")
+    try:
+        env = _reference_env(tmp)
+        out_bed = os.path.join(tmp, "bed.vapor")
+        subprocess.run([sys.executable, os.path.join(REF_PKG, "vapor"), "bed", "--sv-input", ds.bed, "--output-path", os.path.join(tmp, "figs"),
+                        "--output-file", out_bed, "--reference", ds.ref_fa, "--pacbio-input", sam], check=True, env=env, cwd=tmp)
+        shutil.copy(out_bed, os.path.join(case, "svs.bed.vapor.golden"))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    for f in sorted(os.listdir(case)):
+        print("large/" + f, os.path.getsize(os.path.join(case, f)))
+
+
+def _reference_env(tmp):
+    """Scratch package + shims for running the unmodified reference (see main)."""
+    pkg = os.path.join(tmp, "pkgs", "vapor_vali")
+    os.makedirs(pkg)
+    open(os.path.join(pkg, "__init__.py"), "w").close()
+    os.symlink(os.path.join(REF_PKG, "Simple_function.pyx"), os.path.join(pkg, "Simple_function.py"))
+    os.symlink(os.path.join(REF_PKG, "prep.pyx"), os.path.join(pkg, "prep.py"))
+    with open(os.path.join(tmp, "pkgs", "sitecustomize.py"), "w") as f:
+        f.write("import numpy, scipy\nfor _n in ('std', 'mean', 'array', 'sqrt'):\n    if not hasattr(scipy, _n): setattr(scipy, _n, getattr(numpy, _n))\nnumpy.random.seed(0)\n")
+    bindir = os.path.join(tmp, "bin")
+    os.makedirs(bindir)
+    shim = os.path.join(bindir, "samtools")
+    with open(shim, "w") as f:
+        f.write(SHIM % {"root": ROOT})
+    os.chmod(shim, 0o755)
+    env = dict(os.environ)
+    env["PATH"] = bindir + ":" + env["PATH"]
+    env["PYTHONPATH"] = os.path.join(tmp, "pkgs") + ":" + os.path.join(ROOT, "oracle", "mpl_stub")
+    return env
 
 
 if __name__ == "__main__":

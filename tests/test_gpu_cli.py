@@ -28,6 +28,12 @@ def test_bed_cli_matches_reference_golden(tmp_path, session):
     assert session.stats["reads_scored"] > 50
 
 
+def test_bed_cli_large_events_match_reference_golden(tmp_path, session):
+    """Events >= 10 kb: the drivers' junction-window fallbacks (W10 mode) and the long-insertion window, against the
+    table the unmodified reference CLI wrote for tests/golden/cli_case_large."""
+    CC.run_bed_case(tmp_path, session, CC.CASE_LARGE)
+
+
 def test_vcf_cli_matches_reference_golden(tmp_path, session):
     CC.run_vcf_case(tmp_path, session)
 

@@ -92,3 +92,28 @@ def test_distributed_world2_gloo():
     whole = _oracle_scorer(w.batch)
     for f in whole.__dataclass_fields__:
         assert np.array_equal(getattr(whole, f), got[f]), f
+
+
+def test_bam_in_decide_patterns(tmp_path):
+    """One file, or every file of the directory matching an XXX / * pattern (Simple_function.pyx:69-89)."""
+    from vapor_b200 import Simple_function as SF
+    for name in ("s.chr1.bam", "s.chr2.bam", "s.chr1.bai", "other.chr1.bam"):
+        (tmp_path / name).write_text("x")
+    one = str(tmp_path / "s.chr1.bam")
+    assert SF.bam_in_decide(one, None) == [one]
+    assert sorted(SF.bam_in_decide(str(tmp_path / "s.XXX.bam"), None)) == [str(tmp_path / "s.chr1.bam"), str(tmp_path / "s.chr2.bam")]
+    assert sorted(SF.bam_in_decide(str(tmp_path / "s.*.bam"), None)) == [str(tmp_path / "s.chr1.bam"), str(tmp_path / "s.chr2.bam")]
+
+
+def test_small_helpers_match_reference_semantics():
+    from vapor_b200 import Simple_function as SF
+    assert SF.complementary("ACGTNacgtnXRY") == "TGCANtgcan"            # quirk: other characters are dropped
+    assert SF.reverse("ACG") == "GCA"
+    assert SF.flank_length_calculate(["c", 100, 150]) == 50 and SF.flank_length_calculate(["c", 100, 5000]) == 500
+    assert SF.letter_split("c^ba") == ["c^", "b", "a"]
+    assert SF.block_subsplot(["chr1", "10", "20", "chr2", "5", "9"], ["chr1", "chr2"]) == [["chr1", 10, 20], ["chr2", 5, 9]]
+    h = SF.bp_to_chr_hash(["chr1", 100, 200, 300], ["chr1"], 50)
+    assert h["a"] == ["chr1", 100, 200] and h["b"] == ["chr1", 200, 300] and h["+"] == ["chr1", 300, "350"] and h["-"] == ["chr1", "50", 100]
+    assert SF.block_around_check("ba", "ab") == [["-", "b"], ["b", "a"], ["a", "+"]]
+    assert SF.minimize_pacbio_read_list([["r", i % 3, "q"] for i in range(30)])[:10] == [["r", 0, "q"]] * 10
+    assert len(SF.minimize_pacbio_read_list([["r", i % 3, "q"] for i in range(30)])) == 20

@@ -108,3 +108,36 @@ def test_dotdata_property_small_alphabet_strings():
         assert got == exp
 
     check()
+
+
+def test_host_helpers_equal_reference():
+    """The restated host helpers of vapor_b200.Simple_function (they define kernel inputs) against the reference's own
+    functions on random inputs: CIGAR walk, read-list trimming, flank length, block letters, junctions."""
+    from vapor_b200 import Simple_function as SF
+    rng = np.random.default_rng(12)
+    for _ in range(400):
+        n_ops = int(rng.integers(1, 50))
+        ops = rng.choice(list("MIDNSHP=X"), size=n_ops, p=[0.4, 0.15, 0.15, 0.02, 0.05, 0.02, 0.01, 0.1, 0.1])
+        cigar = "".join(f"{int(rng.integers(1, 60))}{o}" for o in ops)
+        a0 = int(rng.integers(1, 9000))
+        start = a0 + int(rng.integers(-20, 900))
+        assert SF.cigar2alignstart_by_pos(cigar, a0, start, start + 1000) == R.cigar2alignstart_by_pos(cigar, a0, start, start + 1000), cigar
+    for _ in range(50):
+        reads = [["r%d" % i, int(rng.integers(0, 6)), "q%d" % i] for i in range(int(rng.integers(0, 60)))]
+        assert SF.minimize_pacbio_read_list(list(reads)) == R.minimize_pacbio_read_list(list(reads))
+    for span in (0, 1, 50, 99, 100, 499, 500, 501, 20000):
+        assert SF.flank_length_calculate(["c", 1000, 1000 + span]) == R.flank_length_calculate(["c", 1000, 1000 + span])
+    for s_ in ("ACGTNacgtnXRYKM", "", "NNNN", "acgtX"):
+        assert SF.complementary(s_) == R.complementary(s_) and SF.reverse(s_) == R.reverse(s_)
+    for let in ("abc", "c^ba", "a^b^", "ab^ab"):
+        assert SF.letter_split(let) == R.letter_split(let)
+    for alt, ref in (("ba", "ab"), ("ab^", "ab"), ("aba", "ab"), ("a", "ab"), ("b^a", "ab"), ("abca", "abc")):
+        assert SF.block_around_check(alt, ref) == R.block_around_check(alt, ref), (alt, ref)
+    chromos = ["chr1", "chr2"]
+    assert SF.block_subsplot(["chr1", "10", "20", "30", "chr2", "5", "9"], chromos) == R.block_subsplot(["chr1", "10", "20", "30", "chr2", "5", "9"], chromos)
+    assert SF.bp_to_chr_hash(["chr1", 100, 200, 300], chromos, 50) == R.bp_to_chr_hash(["chr1", 100, 200, 300], chromos, 50)
+    assert SF.list_unify(["a", "b", "a", "c", "b"]) == R.list_unify(["a", "b", "a", "c", "b"])
+    pin = "chr1 100 id N <DEL> 60 PASS SVTYPE=DEL;END=500;SVLEN=400;SEQ=ACGT;insert_point=chr1:900 GT 0/1".split()
+    for f in ("svtype_extract", "sv_len_extract", "sv_seq_extract", "sv_insert_point_define", "chr_start_end_extract", "INS_length_detect",
+              "polarity_detect"):
+        assert getattr(SF, f)(list(pin)) == getattr(R, f)(list(pin)), f

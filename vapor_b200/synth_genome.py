@@ -141,7 +141,7 @@ def make_dataset(out_dir: str, seed: int = 20261018, n_simple: int = 8, n_comple
                  err: float = 0.15, chrom: str = "chr1", spacing: int = 3000, line_width: int = 60,
                  simple_types: Sequence[str] = ("DEL", "DUP", "INV", "INS"),
                  complex_types: Sequence[str] = ("DEL_INV", "DUP_INV", "DISDUP", "OTHER"),
-                 ins_with_seq_every: int = 2, het_frac: float = 0.5) -> Dataset:
+                 ins_with_seq_every: int = 2, het_frac: float = 0.5, ins_len_override: int = 0) -> Dataset:
     """Write ref.fa(.fai), reads.sam, svs.bed, svs.vcf, truth.json under ``out_dir``."""
     rng = np.random.default_rng(seed)
     os.makedirs(out_dir, exist_ok=True)
@@ -176,7 +176,7 @@ def make_dataset(out_dir: str, seed: int = 20261018, n_simple: int = 8, n_comple
             seg = [("inv", s, e)]; sv = PlantedSV(svid, kind, chrom, s, e, gt)
             span_end = e
         elif kind == "INS":
-            ins = _ACGT[rng.integers(0, 4, size=L, dtype=np.uint8)]
+            ins = _ACGT[rng.integers(0, 4, size=(ins_len_override or L), dtype=np.uint8)]
             seg = [("ins", ins)]
             sv = PlantedSV(svid, kind, chrom, s, s, gt, ins_seq=ins.tobytes().decode(),
                            extra={"with_seq": bool((i // len(simple_types)) % ins_with_seq_every == 0)})
