@@ -118,3 +118,34 @@ def test_figure_hook_writes_dot_lists(tmp_path, session, monkeypatch):
     assert names == {"ref_vs_ref", "alt_vs_alt", "read_vs_ref", "read_vs_alt"}
     diag = [r for r in rows if r[0] == "ref_vs_ref" and r[1] == r[2].strip()]
     assert len(diag) > 1000                                   # the self-plot holds the whole diagonal
+
+
+def test_integration_md_ctypes_stub_runs(engine):
+    """The ctypes stub INTEGRATION.md shows a maintainer of the reference is executed as written (only the library
+    path is made absolute) and must give the same score list and summary as the engine."""
+    import re
+    from vapor_b200 import _native
+    from vapor_b200.engine import Batch, MODE_ABS
+    root = os.path.dirname(CC.HERE)
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(# vapor_vali/_b200\.py.*?)```", md, re.S).group(1)
+    block = block.replace('C.CDLL("libvapor_b200.so")', f'C.CDLL({_native.LIB_PATH!r})')
+    ns = {}
+    exec(compile(block, "INTEGRATION.md:_b200.py", "exec"), ns)
+    rng = np.random.default_rng(31)
+    case = synth.make_sv_case(rng, "INV", 600, genotype=1)
+    ref, alt = case.ref_seq.tobytes().decode(), case.alt_seq.tobytes().decode()
+    reads = []
+    for hap in (case.hap_alt, case.hap_ref, case.hap_alt, case.hap_alt):
+        r, _ = synth.simulate_reads(rng, hap, np.array([0]), np.array([int(case.read_window * 1.12) + 60]), np.array([case.read_window]))
+        reads.append([r.tobytes().decode(), 0, "q"])
+    scores, qs, gs, gt, gq = ns["score_reads"](ref, alt, reads, 10, ns["MODE_ABS"])
+    b = Batch()
+    rid, aid = b.add_seq(ref), b.add_seq(alt)
+    for x in reads:
+        b.add_task(b.add_seq(x[0]), rid, aid, 0, 10, MODE_ABS)
+    b.end_sv("e")
+    pb = b.pack()
+    res = engine.score(pb)
+    assert scores == res.sv_scores(pb, 0) and len(scores) >= 3
+    assert qs == res.sv_qs[0] and gs == res.sv_gs[0] and gt == int(res.sv_gt[0]) and gq == res.sv_gq[0]
