@@ -309,11 +309,19 @@ k2_tile_match(const K2Params p)
         strip = __shfl_sync(0xFFFFFFFFu, strip, 0);
         if (strip >= (unsigned long long)p.n_strips) break;
 
-        // which plot: last index with prefix <= strip
+        // which plot: last index with prefix <= strip.  A 32-ary search, one probe per lane and a vote per level:
+        // 4 dependent global loads for a million plots instead of 20
         int lo = 0, hi = p.n_plots;
         while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if ((unsigned long long)(p.strip_prefix[mid] - p.strip_base) <= strip) lo = mid; else hi = mid;
+            const int span = hi - lo;
+            const int step = (span + 31) >> 5;                       // lane l probes lo + (l+1)*step
+            const int probe = lo + (lane + 1) * step;
+            const bool le = probe < hi && (unsigned long long)(p.strip_prefix[probe] - p.strip_base) <= strip;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, le);       // prefix is non-decreasing: a run of low lanes
+            const int nle = __popc(m);
+            const int new_lo = lo + nle * step;
+            hi = min(hi, new_lo + step);
+            lo = new_lo;
         }
         const Plot pl = p.plots[lo];
         const int local = (int)(strip - (unsigned long long)(p.strip_prefix[lo] - p.strip_base));
