@@ -112,7 +112,8 @@ int vapor_gpu_open(int device, void** handle);
 int vapor_gpu_close(void* handle);
 const char* vapor_gpu_last_error(void* handle);   /* handle may be NULL: last open() error */
 
-/* Tunables: hit-buffer budget in bytes (0 = default) -- bounds device memory per wave. */
+/* Tunables: hit-buffer budget in bytes -- bounds device memory per wave (0 = default: a quarter of the memory free
+ * at open(), at most 24 GB). */
 int vapor_gpu_set_hit_budget(void* handle, int64_t bytes);
 /* Named tunables (none changes a result): "hit_budget_bytes", "tile_variant" (inner loop of the tile
  * kernel: 0 = 16 rows/lane by ISETP only, 1/2/3/4 = 14/16/12/13 rows by ISETP + 2 row polynomials of

@@ -64,6 +64,7 @@ struct Handle {
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t hit_budget = 0;          // bytes; 0 = default
+    int64_t default_hit_budget = (int64_t)6 << 30;
     int k2_ctas_per_sm = 0;          // persistent-grid size of kernel 2 = this x SM count; 0 = occupancy
     int k2_occupancy[K2_NVARIANT] = {0, 0, 0, 0, 0};
     int tile_variant = 4;            // k2 inner-loop variant (k2_variant_*), fixed at upload
@@ -280,7 +281,8 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
         bases += h->ops[i].len;
     }
     // strips + waves (plots were created in task order, so each wave is a contiguous plot range)
-    const int64_t budget_bytes = h->hit_budget > 0 ? h->hit_budget : (int64_t)6 << 30;
+    // hit slab of one wave: a quarter of the device memory free at open(), at most 24 GB, unless the caller set it
+    const int64_t budget_bytes = h->hit_budget > 0 ? h->hit_budget : h->default_hit_budget;
     const int64_t budget_elems = std::max<int64_t>(budget_bytes / (int64_t)sizeof(uint2), 1 << 16);
     h->strip_prefix.assign(h->plots.size() + 1, 0);
     h->plan_variant = h->tile_variant;
@@ -766,6 +768,11 @@ int vapor_gpu_open(int device, void** handle) {
     cudaDeviceProp prop{};
     cudaGetDeviceProperties(&prop, device);
     h->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > 0)
+            h->default_hit_budget = std::max<int64_t>((int64_t)1 << 30, std::min<int64_t>((int64_t)24 << 30, (int64_t)(free_b / 4)));
+    }
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_open_error = cudaGetErrorString(e); delete h; return VAPOR_E_CUDA; }
     build_lut();
