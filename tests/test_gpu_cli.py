@@ -149,3 +149,12 @@ def test_integration_md_ctypes_stub_runs(engine):
     res = engine.score(pb)
     assert scores == res.sv_scores(pb, 0) and len(scores) >= 3
     assert qs == res.sv_qs[0] and gs == res.sv_gs[0] and gt == int(res.sv_gt[0]) and gq == res.sv_gq[0]
+
+
+def test_figure_hook_writes_png(tmp_path, session, monkeypatch):
+    """VAPOR_FIGURES=png: a 2 x 2 recurrence-plot image per event (matplotlib if present, else the built-in writer)."""
+    monkeypatch.setenv("VAPOR_FIGURES", "png")
+    fig = os.path.join(str(tmp_path), "ev.png")
+    SF.vapor_simple_del_Vapor(3, 1, os.path.join(CC.CASE, "reads.sam.gz"), os.path.join(CC.CASE, "ref.fa"), ["chr1", 12000, 12643], fig)
+    data = open(fig, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n" and len(data) > 1000

@@ -762,9 +762,9 @@ def vcf_vapor_modify(vcf_input, vcf_rec_hash_new):
 
 def make_event_figure_1(plt_li, vapor_score_list, best_read_rec, window_size, ref_seq, alt_seq, out_figure_name):
     """The reference draws a 2x2 PNG (ref/ref, alt/alt, best read/ref, best read/alt) per event
-    (Simple_function.pyx:1072-1089).  The four recurrence plots come from the GPU; they are rendered when
-    matplotlib is importable and ``VAPOR_FIGURES`` is ``png``, written as ``<name>.dots.tsv`` when it is ``tsv``,
-    and skipped otherwise (the default: figures are not on the scoring path)."""
+    (Simple_function.pyx:1072-1089).  The four recurrence plots come from the GPU; with ``VAPOR_FIGURES=png`` they are
+    rendered (matplotlib when importable, else a built-in zlib PNG rasteriser), with ``tsv`` written as
+    ``<name>.dots.tsv``, and skipped otherwise (the default: figures are not on the scoring path)."""
     how = os.environ.get("VAPOR_FIGURES", "")
     if how not in ("png", "tsv") or window_size == "Error":
         return
@@ -785,6 +785,7 @@ def make_event_figure_1(plt_li, vapor_score_list, best_read_rec, window_size, re
         matplotlib.use("Agg")
         import matplotlib.pyplot as plt
     except Exception:
+        _write_dotplot_png(out_figure_name, panels)          # no matplotlib: the built-in rasteriser
         return
     fig = plt.figure(plt_li)
     for i, (name, d) in enumerate(panels):
@@ -794,6 +795,32 @@ def make_event_figure_1(plt_li, vapor_score_list, best_read_rec, window_size, re
         ax.set_title(name, fontsize=8)
     fig.savefig(out_figure_name)
     plt.close(fig)
+
+
+def _write_dotplot_png(path, panels, side=360, pad=12):
+    """2 x 2 recurrence plots as an 8-bit grey PNG, written with zlib only (x = structure position to the right,
+    y = read position upwards, as in the reference's figure)."""
+    import struct
+    import zlib
+    W = H = 2 * side + 3 * pad
+    img = np.full((H, W), 255, dtype=np.uint8)
+    for i, (_name, d) in enumerate(panels):
+        r0, c0 = pad + (i // 2) * (side + pad), pad + (i % 2) * (side + pad)
+        img[r0 - 1:r0 + side + 1, c0 - 1] = 0; img[r0 - 1:r0 + side + 1, c0 + side] = 0
+        img[r0 - 1, c0 - 1:c0 + side + 1] = 0; img[r0 + side, c0 - 1:c0 + side + 1] = 0
+        if len(d):
+            d = np.asarray(d, dtype=np.int64)
+            span = max(int(d.max()) + 1, 1)
+            px = c0 + (d[:, 0] * side) // span
+            py = r0 + side - 1 - (d[:, 1] * side) // span
+            img[py, px] = 0
+    raw = b"".join(b"\x00" + img[r].tobytes() for r in range(H))
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, 8, 0, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
 
 
 # ====================================================================================================
