@@ -788,6 +788,9 @@ def make_event_figure_1(plt_li, vapor_score_list, best_read_rec, window_size, re
         _write_dotplot_png(out_figure_name, panels)          # no matplotlib: the built-in rasteriser
         return
     fig = plt.figure(plt_li)
+    if not hasattr(fig, "add_subplot"):                          # a stand-in matplotlib (tests stub it out)
+        _write_dotplot_png(out_figure_name, panels)
+        return
     for i, (name, d) in enumerate(panels):
         ax = fig.add_subplot(2, 2, i + 1)
         if len(d):

@@ -46,16 +46,20 @@ __host__ __device__ __forceinline__ uint32_t mix30(uint32_t x) {
     return x;
 }
 
-// Word of one k-mer the slow way (k > 15, or a k-mer holding N / lower case): symmetric hash of the forward and the
-// reverse-complement strings, palindromes confirmed exactly.  `w` points at the k codes of the k-mer.
-__device__ __forceinline__ uint32_t k1_hashed_word(const uint8_t* w, int k, bool& pal) {
-    const uint64_t B = 0x9E3779B97F4A7C15ull | 1ull;
-    uint64_t f = 0, r = 0;
-    #pragma unroll 1
-    for (int t = 0; t < k; ++t) {
-        f = f * B + (uint64_t)(w[t] + 1);
-        r = r * B + (uint64_t)(comp_code(w[k - 1 - t]) + 1);
-    }
+// Hashed words (k > 15, or a k-mer holding N / lower case).  The k-mer and its reverse complement are hashed as
+// polynomials over Z/2^64 -- f = sum (c_t + 1) B^(k-1-t), r = sum (comp(c_t) + 1) B^t -- and the word is a symmetric
+// mix of the two, so that a k-mer and its reverse complement get the same word.  Both sums can be *rolled* from one
+// position to the next (multiply by B, resp. by B^-1): O(1) per position.
+constexpr uint64_t K1_B = 0x9E3779B97F4A7C15ull | 1ull;
+
+__device__ __forceinline__ uint64_t k1_inv64(uint64_t b) {       // inverse of an odd number mod 2^64 (Newton)
+    uint64_t x = b;                                              // b*b = 1 mod 8
+    #pragma unroll
+    for (int i = 0; i < 5; ++i) x *= 2ull - b * x;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t k1_hash_finish(uint64_t f, uint64_t r, const uint8_t* w, int k, bool& pal) {
     pal = false;
     if (f == r) {                          // candidate palindrome: confirm exactly
         pal = true;
@@ -66,6 +70,17 @@ __device__ __forceinline__ uint32_t k1_hashed_word(const uint8_t* w, int k, bool
     uint32_t h = H_NEEDS_VERIFY | (pal ? H_PALINDROME : 0u) | h30;
     if (h > H_MAX_VALID) h -= 4;
     return h;
+}
+
+// one k-mer from scratch (k <= 15 windows that hold N / lower case: rare)
+__device__ __forceinline__ uint32_t k1_hashed_word(const uint8_t* w, int k, bool& pal) {
+    uint64_t f = 0, r = 0;
+    #pragma unroll 1
+    for (int t = 0; t < k; ++t) {
+        f = f * K1_B + (uint64_t)(w[t] + 1);
+        r = r * K1_B + (uint64_t)(comp_code(w[k - 1 - t]) + 1);
+    }
+    return k1_hash_finish(f, r, w, k, pal);
 }
 
 constexpr int K1_RUN = K1_CHUNK / K1_THREADS;      // consecutive positions per thread (8)
@@ -128,14 +143,24 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
         const bool exact_k = k <= 15;
         const uint32_t mask = exact_k ? ((k == 16 ? 0u : (1u << (2 * k))) - 1u) : 0u;
         uint32_t f = 0, r = 0;
+        uint64_t hf = 0, hr = 0, bk1 = 1, binv = 0;              // k > 15: rolling polynomial hashes, B^(k-1), B^-1
         int n_np = 0, n_inv = 0;
         if (p0 < npos_hash) {
+            if (!exact_k) {
+                for (int t = 1; t < k; ++t) bk1 *= K1_B;
+                binv = k1_inv64(K1_B);
+            }
+            uint64_t bt = 1;                                     // B^t
             for (int t = 0; t < k; ++t) {
                 const int c = s_code[p0 + t];
                 n_np += (c >= 4); n_inv += (c == CODE_INVALID);
                 if (exact_k) {
                     f = ((f << 2) | (uint32_t)(c & 3)) & mask;
                     r = (r >> 2) | ((uint32_t)(3 - (c & 3)) << (2 * (k - 1)));
+                } else {
+                    hf = hf * K1_B + (uint64_t)(c + 1);
+                    hr += (uint64_t)(comp_code(c) + 1) * bt;
+                    bt *= K1_B;
                 }
             }
         }
@@ -151,8 +176,10 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
                 } else if (exact_k && n_np == 0) {
                     pal = (f == r);
                     h = mix30(min(f, r)) | (pal ? H_PALINDROME : 0u);
-                } else {
+                } else if (exact_k) {
                     h = k1_hashed_word(s_code + p, k, pal);
+                } else {
+                    h = k1_hash_finish(hf, hr, s_code + p, k, pal);
                 }
                 if (p + 1 < npos_hash) {                           // roll the window one base on
                     const int cn = s_code[p + k];
@@ -161,6 +188,9 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
                     if (exact_k) {
                         f = ((f << 2) | (uint32_t)(cn & 3)) & mask;
                         r = (r >> 2) | ((uint32_t)(3 - (cn & 3)) << (2 * (k - 1)));
+                    } else {
+                        hf = (hf - (uint64_t)(c0 + 1) * bk1) * K1_B + (uint64_t)(cn + 1);
+                        hr = (hr - (uint64_t)(comp_code(c0) + 1)) * binv + (uint64_t)(comp_code(cn) + 1) * bk1;
                     }
                 }
             }
