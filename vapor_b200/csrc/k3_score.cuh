@@ -511,11 +511,13 @@ struct K3Params {
 // kernel calls this function from one call site: fully inlined and unrolled the kernel was 318 KB of code and spent
 // more time waiting for instruction fetch than for anything else.
 __device__ void k3_eval(int mode, const PlotView* pv /*[2]: ref, alt*/, int len_ref, int len_alt,
-                        K3Scratch& s, K3Shared& sh, EvalResult& out, unsigned long long* cs /*[2]*/)
+                        K3Scratch& s, K3Shared& sh, EvalResult& out, unsigned long long* cs /*[2]*/,
+                        int* minx /*[2]*/, int* maxx /*[2]*/, bool have_pass0)
 {
-    int minx[2], maxx[2];
-    #pragma unroll 1
-    for (int w = 0; w < 2; ++w) k3_pass0(pv[w], sh, minx[w], maxx[w], cs[w]);
+    if (!have_pass0) {                                 // spans + checksums; the caller hands them over when it has them
+        #pragma unroll 1
+        for (int w = 0; w < 2; ++w) k3_pass0(pv[w], sh, minx[w], maxx[w], cs[w]);
+    }
     out.a = 0; out.b = 0; out.valid = false;
     const double Hr = (double)pv[0].H, Ha = (double)pv[1].H;
     const double Lr = (double)len_ref, La = (double)len_alt;
@@ -583,9 +585,15 @@ k3_score_reads(const K3Params p)
         unsigned long long cs[4] = {0, 0, 0, 0};
         if (!bad) {
             const int n_eval = (t.mode == 3) ? 2 : 1;                   // the simple-DEL rule asks ABS, then W10
+            int minx[4], maxx[4];
             #pragma unroll 1
-            for (int e = 0; e < n_eval; ++e)
-                k3_eval((t.mode == 3) ? e : t.mode, pv + 2 * e, t.len_ref, t.len_alt, s, sh, ev[e], cs + 2 * e);
+            for (int e = 0; e < n_eval; ++e) {
+                // the W10 opinion of the simple-DEL rule looks at the same two plots unless the structures hold lower case
+                const bool same = e == 1 && t.plot[2] == t.plot[0] && t.plot[3] == t.plot[1];
+                if (same) { minx[2] = minx[0]; maxx[2] = maxx[0]; minx[3] = minx[1]; maxx[3] = maxx[1]; cs[2] = cs[0]; cs[3] = cs[1]; }
+                k3_eval((t.mode == 3) ? e : t.mode, pv + 2 * e, t.len_ref, t.len_alt, s, sh, ev[e], cs + 2 * e,
+                        minx + 2 * e, maxx + 2 * e, same);
+            }
         }
         const EvalResult ea = ev[0], eb = ev[1];
         if (threadIdx.x == 0) {
