@@ -85,6 +85,102 @@ __device__ __forceinline__ uint32_t k1_hashed_word(const uint8_t* w, int k, bool
 
 constexpr int K1_RUN = K1_CHUNK / K1_THREADS;      // consecutive positions per thread (8)
 
+// Words and codes of one thread's run of K1_RUN positions.  EXACT: k <= 15 (rolling 2-bit words), else rolling
+// polynomial hashes; two instantiations so that neither carries the other's state in registers.
+template <bool EXACT>
+__device__ __forceinline__ bool k1_run(const uint8_t* s_code, const Operand& op, int base0, int k,
+                                       uint32_t* __restrict__ hash, uint8_t* __restrict__ code)
+{
+    const int npos_code = min(K1_CHUNK, op.len - base0);          // bases owned by this chunk
+    const int npos_hash = min(K1_CHUNK, op.n - base0);            // k-mers owned by this chunk (may be <= 0)
+    const bool is_read = (op.flags & OPF_READ) != 0;
+    bool bad_read = false;
+    const int p0 = threadIdx.x * K1_RUN;
+    if (p0 < npos_code) {
+        uint32_t words[K1_RUN];
+        uint8_t codes[K1_RUN];
+        // rolling state of the window [p, p+k): 2-bit forward / reverse-complement words (k <= 15), how many of its
+        // codes are not plain ACGT, how many are invalid
+        const uint32_t mask = EXACT ? ((k == 16 ? 0u : (1u << (2 * k))) - 1u) : 0u;
+        uint32_t f = 0, r = 0;
+        uint64_t hf = 0, hr = 0, bk1 = 1, binv = 0;              // k > 15: rolling polynomial hashes, B^(k-1), B^-1
+        int n_np = 0, n_inv = 0;
+        if (p0 < npos_hash) {
+            if (!EXACT) {
+                for (int t = 1; t < k; ++t) bk1 *= K1_B;
+                binv = k1_inv64(K1_B);
+            }
+            uint64_t bt = 1;                                     // B^t
+            for (int t = 0; t < k; ++t) {
+                const int c = s_code[p0 + t];
+                n_np += (c >= 4); n_inv += (c == CODE_INVALID);
+                if (EXACT) {
+                    f = ((f << 2) | (uint32_t)(c & 3)) & mask;
+                    r = (r >> 2) | ((uint32_t)(3 - (c & 3)) << (2 * (k - 1)));
+                } else {
+                    hf = hf * K1_B + (uint64_t)(c + 1);
+                    hr += (uint64_t)(comp_code(c) + 1) * bt;
+                    bt *= K1_B;
+                }
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < K1_RUN; ++i) {
+            const int p = p0 + i;
+            const int c0 = (p < npos_code) ? s_code[p] : 0;
+            uint32_t h = H_STRUCT_INVALID;
+            bool pal = false;
+            if (p < npos_hash) {
+                if (n_inv > 0) {
+                    if (is_read) { bad_read = true; h = H_READ_PAD; }
+                } else if (EXACT && n_np == 0) {
+                    pal = (f == r);
+                    h = mix30(min(f, r)) | (pal ? H_PALINDROME : 0u);
+                } else if (EXACT) {
+                    h = k1_hashed_word(s_code + p, k, pal);
+                } else {
+                    h = k1_hash_finish(hf, hr, s_code + p, k, pal);
+                }
+                if (p + 1 < npos_hash) {                           // roll the window one base on
+                    const int cn = s_code[p + k];
+                    n_np += (cn >= 4) - (c0 >= 4);
+                    n_inv += (cn == CODE_INVALID) - (c0 == CODE_INVALID);
+                    if (EXACT) {
+                        f = ((f << 2) | (uint32_t)(cn & 3)) & mask;
+                        r = (r >> 2) | ((uint32_t)(3 - (cn & 3)) << (2 * (k - 1)));
+                    } else {
+                        hf = (hf - (uint64_t)(c0 + 1) * bk1) * K1_B + (uint64_t)(cn + 1);
+                        hr = (hr - (uint64_t)(comp_code(c0) + 1)) * binv + (uint64_t)(comp_code(cn) + 1) * bk1;
+                    }
+                }
+            }
+            words[i] = h;
+            codes[i] = (uint8_t)(c0 | (pal ? 0x80 : 0));
+        }
+        // ---- stores: 8 words = two 16-byte stores, 8 codes = one 8-byte store when the run is complete --------
+        uint32_t* hp = hash + op.hash_off + base0 + p0;
+        uint8_t* cp = code + op.code_off + base0 + p0;
+        if (p0 + K1_RUN <= npos_hash) {
+            reinterpret_cast<uint4*>(hp)[0] = make_uint4(words[0], words[1], words[2], words[3]);
+            reinterpret_cast<uint4*>(hp)[1] = make_uint4(words[4], words[5], words[6], words[7]);
+        } else {
+            #pragma unroll
+            for (int i = 0; i < K1_RUN; ++i) if (p0 + i < npos_hash) hp[i] = words[i];
+        }
+        if (p0 + K1_RUN <= npos_code) {
+            uint2 v;
+            v.x = codes[0] | (codes[1] << 8) | (codes[2] << 16) | ((uint32_t)codes[3] << 24);
+            v.y = codes[4] | (codes[5] << 8) | (codes[6] << 16) | ((uint32_t)codes[7] << 24);
+            *reinterpret_cast<uint2*>(cp) = v;
+        } else {
+            #pragma unroll
+            for (int i = 0; i < K1_RUN; ++i) if (p0 + i < npos_code) cp[i] = codes[i];
+        }
+    }
+    return bad_read;
+}
+
+
 __global__ void __launch_bounds__(K1_THREADS)
 k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
               const int32_t* __restrict__ chunk_prefix,   // [n_ops+1] cumulative chunk counts
@@ -130,93 +226,7 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
     __syncthreads();
     const uint8_t* s_code = s_raw + head;
 
-    const int npos_code = min(K1_CHUNK, op.len - base0);          // bases owned by this chunk
-    const int npos_hash = min(K1_CHUNK, op.n - base0);            // k-mers owned by this chunk (may be <= 0)
-    const bool is_read = (op.flags & OPF_READ) != 0;
-    bool bad_read = false;
-    const int p0 = threadIdx.x * K1_RUN;
-    if (p0 < npos_code) {
-        uint32_t words[K1_RUN];
-        uint8_t codes[K1_RUN];
-        // rolling state of the window [p, p+k): 2-bit forward / reverse-complement words (k <= 15), how many of its
-        // codes are not plain ACGT, how many are invalid
-        const bool exact_k = k <= 15;
-        const uint32_t mask = exact_k ? ((k == 16 ? 0u : (1u << (2 * k))) - 1u) : 0u;
-        uint32_t f = 0, r = 0;
-        uint64_t hf = 0, hr = 0, bk1 = 1, binv = 0;              // k > 15: rolling polynomial hashes, B^(k-1), B^-1
-        int n_np = 0, n_inv = 0;
-        if (p0 < npos_hash) {
-            if (!exact_k) {
-                for (int t = 1; t < k; ++t) bk1 *= K1_B;
-                binv = k1_inv64(K1_B);
-            }
-            uint64_t bt = 1;                                     // B^t
-            for (int t = 0; t < k; ++t) {
-                const int c = s_code[p0 + t];
-                n_np += (c >= 4); n_inv += (c == CODE_INVALID);
-                if (exact_k) {
-                    f = ((f << 2) | (uint32_t)(c & 3)) & mask;
-                    r = (r >> 2) | ((uint32_t)(3 - (c & 3)) << (2 * (k - 1)));
-                } else {
-                    hf = hf * K1_B + (uint64_t)(c + 1);
-                    hr += (uint64_t)(comp_code(c) + 1) * bt;
-                    bt *= K1_B;
-                }
-            }
-        }
-        #pragma unroll
-        for (int i = 0; i < K1_RUN; ++i) {
-            const int p = p0 + i;
-            const int c0 = (p < npos_code) ? s_code[p] : 0;
-            uint32_t h = H_STRUCT_INVALID;
-            bool pal = false;
-            if (p < npos_hash) {
-                if (n_inv > 0) {
-                    if (is_read) { bad_read = true; h = H_READ_PAD; }
-                } else if (exact_k && n_np == 0) {
-                    pal = (f == r);
-                    h = mix30(min(f, r)) | (pal ? H_PALINDROME : 0u);
-                } else if (exact_k) {
-                    h = k1_hashed_word(s_code + p, k, pal);
-                } else {
-                    h = k1_hash_finish(hf, hr, s_code + p, k, pal);
-                }
-                if (p + 1 < npos_hash) {                           // roll the window one base on
-                    const int cn = s_code[p + k];
-                    n_np += (cn >= 4) - (c0 >= 4);
-                    n_inv += (cn == CODE_INVALID) - (c0 == CODE_INVALID);
-                    if (exact_k) {
-                        f = ((f << 2) | (uint32_t)(cn & 3)) & mask;
-                        r = (r >> 2) | ((uint32_t)(3 - (cn & 3)) << (2 * (k - 1)));
-                    } else {
-                        hf = (hf - (uint64_t)(c0 + 1) * bk1) * K1_B + (uint64_t)(cn + 1);
-                        hr = (hr - (uint64_t)(comp_code(c0) + 1)) * binv + (uint64_t)(comp_code(cn) + 1) * bk1;
-                    }
-                }
-            }
-            words[i] = h;
-            codes[i] = (uint8_t)(c0 | (pal ? 0x80 : 0));
-        }
-        // ---- stores: 8 words = two 16-byte stores, 8 codes = one 8-byte store when the run is complete --------
-        uint32_t* hp = hash + op.hash_off + base0 + p0;
-        uint8_t* cp = code + op.code_off + base0 + p0;
-        if (p0 + K1_RUN <= npos_hash) {
-            reinterpret_cast<uint4*>(hp)[0] = make_uint4(words[0], words[1], words[2], words[3]);
-            reinterpret_cast<uint4*>(hp)[1] = make_uint4(words[4], words[5], words[6], words[7]);
-        } else {
-            #pragma unroll
-            for (int i = 0; i < K1_RUN; ++i) if (p0 + i < npos_hash) hp[i] = words[i];
-        }
-        if (p0 + K1_RUN <= npos_code) {
-            uint2 v;
-            v.x = codes[0] | (codes[1] << 8) | (codes[2] << 16) | ((uint32_t)codes[3] << 24);
-            v.y = codes[4] | (codes[5] << 8) | (codes[6] << 16) | ((uint32_t)codes[7] << 24);
-            *reinterpret_cast<uint2*>(cp) = v;
-        } else {
-            #pragma unroll
-            for (int i = 0; i < K1_RUN; ++i) if (p0 + i < npos_code) cp[i] = codes[i];
-        }
-    }
+    const bool bad_read = (k <= 15) ? k1_run<true>(s_code, op, base0, k, hash, code) : k1_run<false>(s_code, op, base0, k, hash, code);
     if (bad_read) atomicOr(&op_status[lo], 1);
 }
 
