@@ -63,3 +63,28 @@ def test_vcf_with_header_annotates_the_right_records(tmp_path, session):
         assert ("VaPor_GT=" in g) == ("VaPor_GT=" in e)
     assert got[0].startswith("##fileformat")
     assert sum(1 for l in got if l.startswith("##INFO=<ID=VaPoR_")) == 4
+
+
+def test_svelter_subcommand_matches_vcf_other_path(tmp_path, session):
+    """`vapor svelter` (vapor_vali/vapor:467-492) drives the same CANNOT_CLASSIFY driver as the VCF 'Other=' records:
+    the same event through both entry points gives the same scores."""
+    import json
+    truth = json.load(open(os.path.join(CC.CASE, "truth.json")))
+    ev = [t for t in truth if t["type"] == "OTHER"][0]
+    b0, b1, b2 = ev["bps"]
+    sv = os.path.join(str(tmp_path), "calls.svelter")
+    with open(sv, "w") as f:
+        f.write("chr\tstart\tend\tbp_info\tref\talt\n")
+        f.write(f"chr1\t{b0}\t{b2}\tchr1:{b0}:{b1}:{b2}\tab/ab\tab/ba\n")
+    out = os.path.join(str(tmp_path), "svelter.vapor")
+    args = CC.Args(sv_input=sv, output_path=os.path.join(str(tmp_path), "figs"), output_file=out,
+                   reference=os.path.join(CC.CASE, "ref.fa"), pacbio_input=os.path.join(CC.CASE, "reads.sam.gz"))
+    SF.set_session(session)
+    try:
+        cli.run_svelter(args, [session])
+    finally:
+        SF.set_session(None)
+    row = open(out).read().strip().split("\t")
+    gold = [l.rstrip("\n").split("\t") for l in open(os.path.join(CC.CASE, "svs_nohdr.vcf.vapor.golden")) if "<OTHER>" in l][0]
+    rec = [kv for kv in gold[7].split(";") if kv.startswith("VaPor_REC=")][0].split("=", 1)[1]
+    assert row[0] == f".chr1_{b0}_{b1}_{b2}" and row[-1] == rec
