@@ -56,7 +56,7 @@ struct Wave {
 
 // kernel-3 scratch classes: bins that fit in shared memory, then a global-memory fallback
 constexpr int K3_NCLASS = 5;
-const int k3_class_cap[K3_NCLASS - 1] = {4096, 16384, 49152, 110000};
+const int k3_class_cap[K3_NCLASS - 1] = {4096, 16384, 26624, 110000};
 
 struct Handle {
     int device = 0;
