@@ -561,7 +561,11 @@ __device__ void k3_eval(int mode, const PlotView* pv /*[2]: ref, alt*/, int len_
     out.valid = (out.a != 0.0) && (out.b != 0.0);       // `if not 0 in pair`
 }
 
-__global__ void __launch_bounds__(K3_THREADS)
+#ifndef K3_MINB
+#define K3_MINB 6                              // measured: 6 resident CTAs per SM (42 registers) beats 4 (64)
+#endif
+
+__global__ void __launch_bounds__(K3_THREADS, K3_MINB)
 k3_score_reads(const K3Params p)
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];
