@@ -181,7 +181,11 @@ __device__ __forceinline__ bool k1_run(const uint8_t* s_code, const Operand& op,
 }
 
 
-__global__ void __launch_bounds__(K1_THREADS)
+#ifndef K1_MINB
+#define K1_MINB 8                              // measured: 8 resident CTAs per SM (32 registers)
+#endif
+
+__global__ void __launch_bounds__(K1_THREADS, K1_MINB)
 k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
               const int32_t* __restrict__ chunk_prefix,   // [n_ops+1] cumulative chunk counts
               int n_ops, uint32_t* __restrict__ hash, uint8_t* __restrict__ code,
