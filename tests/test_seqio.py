@@ -93,3 +93,20 @@ def test_cigar_table_walk_equals_plain_walk():
             exp = [rr - sd, 0] if (last != "" and last in "M=") else [rr, sd]
             assert SF.cigar2alignstart_by_pos(cigar, a0, start, start + 1000) == exp, (cigar, a0, start)
     assert SF.cigar2alignstart_by_pos("*", 10, 20, 30) == [0, -10]
+
+
+def test_sam_text_multi_contig_and_unsorted(tmp_path):
+    """Records of several contigs, not coordinate-sorted: fetch still returns exactly the overlapping ones, in file order."""
+    sam = tmp_path / "u.sam"
+    recs = [("a", "c2", 500, "100M"), ("b", "c1", 900, "50M20D50M"), ("c", "c1", 100, "10S80M"), ("d", "c1", 950, "*"),
+            ("e", "c2", 10, "30M"), ("f", "c1", 880, "30M")]
+    with open(sam, "w") as f:
+        f.write("@HD\tVN:1.6\n")
+        for q, c, p, cg in recs:
+            f.write(f"{q}\t0\t{c}\t{p}\t60\t{cg}\t*\t0\t0\t{'ACGT' * 30}\t*\n")
+    af = seqio.AlignmentFile(str(sam))
+    assert [r.qname for r in af.fetch("c1", 905, 960)] == ["b", "d", "f"]
+    assert [r.qname for r in af.fetch("c1", 1, 99)] == []
+    assert [r.qname for r in af.fetch("c1", 179, 179)] == ["c"]            # soft clip does not extend the span: 100..179
+    assert [r.qname for r in af.fetch("c1", 180, 180)] == []
+    assert [r.qname for r in af.fetch("c2", 1, 10000)] == ["a", "e"]
