@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VAPOR_B200_ABI_VERSION 1
+#define VAPOR_B200_ABI_VERSION 2
 
 /* error codes */
 #define VAPOR_OK            0
@@ -102,7 +102,11 @@ typedef struct vapor_timings {
     int64_t n_plots, n_operands, n_strips, n_waves, n_overflow_plots;
     int64_t launches;            /* kernels launched by the last run                     */
     int64_t bases;               /* bases packed by kernel 1                             */
-    int64_t padded_cells;        /* cells the tile kernel evaluates, strip padding included */
+    int64_t padded_cells;        /* cells the all-pairs tile kernel evaluates, strip padding included (k2_mode 0) */
+    int64_t evaluated_cells;     /* word compares kernel 2 really made: padded_cells for the tile kernel; for the join
+                                    kernel the sum over read k-mers of the size of the table bucket they fall into */
+    float   table_ms;            /* kernel 1b: sorted word tables of the structure-side operands (k2_mode 1) */
+    int32_t k2_mode;             /* kernel-2 variant the last plan was made for */
 } vapor_timings_t;
 
 /* Open one handle on CUDA device `device`.  One handle per device/thread; a handle is
@@ -115,9 +119,12 @@ const char* vapor_gpu_last_error(void* handle);   /* handle may be NULL: last op
 /* Tunables: hit-buffer budget in bytes -- bounds device memory per wave (0 = default: a quarter of the memory free
  * at open(), at most 24 GB). */
 int vapor_gpu_set_hit_budget(void* handle, int64_t bytes);
-/* Named tunables (none changes a result): "hit_budget_bytes", "tile_variant" (inner loop of the tile
+/* Named tunables (none changes a result): "hit_budget_bytes"; "k2_mode" (kernel 2: 1 = radix-partitioned join,
+ * the default -- only cells whose k-mer words share a bucket are compared; 0 = all-pairs tile kernel -- every cell
+ * of every plot is compared; both emit the identical hit set); "tile_variant" (inner loop of the tile
  * kernel: 0 = 16 rows/lane by ISETP only, 1/2/3/4 = 14/16/12/13 rows by ISETP + 2 row polynomials of
- * 8 rows by IMAD; default 4), "k2_ctas_per_sm" (persistent-grid size).  Takes effect at the next upload. */
+ * 8 rows by IMAD; default 4), "k2_ctas_per_sm" (persistent-grid size of the tile kernel), "plan_threads" (host
+ * threads used for planning, 0 = auto).  Takes effect at the next upload. */
 int vapor_gpu_set_option(void* handle, const char* name, int64_t value);
 
 /* Blocking one-shot: host prep + H2D + kernels 1-4 + D2H.

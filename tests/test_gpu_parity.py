@@ -85,6 +85,64 @@ def test_dotdata_repetitive_overflow(engine):
     np.testing.assert_array_equal(got, exp)
 
 
+def test_overflowing_waves_then_second_run(engine):
+    """Repetitive plots (more dots than the first-pass capacity n + m + 32) in several waves of one resident batch,
+    scored twice: the overflow re-run must not touch the resident plan (stale hit offsets after the
+    overflow buffer was reallocated), so run() #2 equals run() #1 equals the oracle."""
+    from vapor_b200.engine import Engine
+    rng = np.random.default_rng(23)
+    b = Batch()
+    unit = synth.random_dna(rng, 37)
+    for rep, extra in ((30, 0), (12, 1), (45, 2), (20, 0)):
+        ref = np.concatenate([synth.random_dna(rng, 2500), np.tile(unit, rep), synth.random_dna(rng, 2500)])
+        alt = np.concatenate([ref[:2600], np.tile(unit, rep + 8), ref[-2550:]])
+        rid, aid = b.add_seq(ref), b.add_seq(alt)
+        for j in range(3):
+            read = np.concatenate([ref[: 2500 + 10 * j], np.tile(unit, rep + j), ref[-2500:]])
+            b.add_task(b.add_seq(read), rid, aid, extra, 10, (MODE_ABS, MODE_W10, MODE_REDEF)[j])
+        b.end_sv(rep)
+    for _ in range(2):                                      # ordinary SVs between and after the repetitive ones
+        case = synth.make_sv_case(rng, "DEL", 400, genotype=1)
+        rid, aid = b.add_seq(case.ref_seq), b.add_seq(case.alt_seq)
+        reads, _ = synth.simulate_reads(rng, case.hap_alt, np.array([0]), np.array([1100]), np.array([case.read_window]))
+        b.add_task(b.add_seq(reads), rid, aid, 0, 10, MODE_ABS_AND_W10)
+        b.end_sv("DEL")
+    pb = b.pack()
+    exp = BO.score_batch(pb)
+    eng = Engine(0, hit_budget_bytes=1 << 16)               # smallest budget: about one task per wave
+    try:
+        eng.set_option("k2_mode", 1 if engine.k2_mode_name == "join" else 0)
+        eng.upload(pb)
+        eng.run()
+        tm = eng.timings()
+        assert tm["n_waves"] > 2 and tm["n_overflow_plots"] >= 4
+        first = eng.fetch()
+        eng.run()
+        assert eng.timings()["n_overflow_plots"] == tm["n_overflow_plots"]
+        second = eng.fetch()
+    finally:
+        eng.close()
+    _compare(first, exp)
+    for f in first.__dataclass_fields__:
+        np.testing.assert_array_equal(getattr(second, f), getattr(first, f), err_msg=f)
+
+
+def test_negative_miss_bp_slices_from_the_end(engine):
+    """cigar2alignstart_by_pos can hand back a negative miss_bp; the reference then slices ref_seq[miss_bp:] the
+    Python way (Simple_function.pyx:185-186).  The library does the same instead of rejecting the batch."""
+    rng = np.random.default_rng(29)
+    case = synth.make_sv_case(rng, "INV", 500, genotype=1)
+    b = Batch()
+    rid, aid = b.add_seq(case.ref_seq), b.add_seq(case.alt_seq)
+    reads, _ = synth.simulate_reads(rng, case.hap_alt, np.array([0]), np.array([1300]), np.array([700]))
+    for miss in (-700, -5, -100000, 0):
+        b.add_task(b.add_seq(reads), rid, aid, miss, 10, MODE_ABS)
+        b.add_task(b.add_seq(reads), rid, aid, miss, 10, MODE_W10)
+    b.end_sv("neg")
+    pb = b.pack()
+    _compare(engine.score(pb), BO.score_batch(pb))
+
+
 @pytest.mark.parametrize("seed,types", [(1, synth.SV_TYPES), (2, ("DEL",)), (3, ("TANDUP", "INV")), (4, ("INS",))])
 def test_workload_parity(engine, seed, types):
     w = synth.make_workload(12, seed=seed, types=types, size_range=(50, 1500), reads_per_sv=8,
@@ -136,6 +194,7 @@ def test_hit_budget_waves_identical(engine):
     base = engine.score(w.batch)
     small = Engine(0, hit_budget_bytes=1 << 20)         # force many waves
     try:
+        small.set_option("k2_mode", 1 if engine.k2_mode_name == "join" else 0)
         res = small.score(w.batch)
         assert small.timings()["n_waves"] > 1
     finally:
@@ -201,8 +260,9 @@ def test_large_windows(engine, svtype, svlen, k, mode):
 def test_properties_at_benchmark_scale(engine):
     """Size-independent properties on a batch too large for the oracle to score in full (BASELINE config 2 sizes):
     (1) waves: a 64 MB hit budget (many waves) gives byte-identical results to one wave; (2) sharding: scoring the
-    SVs in two halves and merging equals scoring them together; (3) the tile variants (ISETP-only vs dual-pipe
-    inner loop) give identical hit counts and coordinate checksums; (4) a sample of SVs agrees with the oracle."""
+    SVs in two halves and merging equals scoring them together; (3) the kernel-2 variants (join kernel, all-pairs tile
+    kernel with the ISETP-only and the dual-pipe inner loop) give identical hit counts and coordinate checksums;
+    (4) a sample of SVs agrees with the oracle."""
     from vapor_b200 import multi
     from vapor_b200.engine import Engine
     w = synth.make_workload(120, seed=77, size_range=(50, 5000), reads_per_sv=20)
@@ -210,15 +270,23 @@ def test_properties_at_benchmark_scale(engine):
     assert (base.task_status == 1).sum() > 0.5 * w.batch.n_task
     small = Engine(0, hit_budget_bytes=64 << 20)
     try:
+        small.set_option("k2_mode", 1 if engine.k2_mode_name == "join" else 0)
         waves = small.score(w.batch)
         assert small.timings()["n_waves"] > 1
+        small.set_option("k2_mode", 0)
         small.set_option("tile_variant", 0)
         v0 = small.score(w.batch)
+        small.set_option("tile_variant", 4)
+        v4 = small.score(w.batch)
+        small.set_option("k2_mode", 1)
+        vj = small.score(w.batch)
+        tmj = small.timings()
+        assert tmj["k2_mode"] == 1 and 0 < tmj["evaluated_cells"] < tmj["cells"] // 100
     finally:
         small.close()
     for f in base.__dataclass_fields__:
-        np.testing.assert_array_equal(getattr(waves, f), getattr(base, f), err_msg=f)
-        np.testing.assert_array_equal(getattr(v0, f), getattr(base, f), err_msg=f)
+        for other in (waves, v0, v4, vj):
+            np.testing.assert_array_equal(getattr(other, f), getattr(base, f), err_msg=f)
     import threading
     lock = threading.Lock()                                  # one handle is not re-entrant: serialise the two shards
 

@@ -12,7 +12,7 @@ SOURCES = ["api.cu"]
 HEADERS = ["common.cuh", "k1_pack.cuh", "k2_tile.cuh", "k3_score.cuh", "k4_genotype.cuh",
            os.path.join("..", "..", "include", "vapor_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 
 def _nvcc() -> str:

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "k1_pack.cuh"
 #include "k2_tile.cuh"
+#include "k2_join.cuh"
 #include "k3_score.cuh"
 #include "k4_genotype.cuh"
 
@@ -14,7 +15,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace vb;
@@ -58,17 +61,32 @@ struct Wave {
 constexpr int K3_NCLASS = 5;
 const int k3_class_cap[K3_NCLASS - 1] = {4096, 16384, 26624, 110000};
 
+// join-kernel launch classes by table blob size (dynamic shared memory of the launch)
+constexpr int K2J_NCLASS = 3;
+const int k2j_class_cap[K2J_NCLASS] = {16640, 45056, 81936};
+
+// the k2 plan of a set of plots: strips for the tile kernel, or table chunks + items for the join kernel
+struct JoinPlan {
+    std::vector<JoinItem> items;                 // grouped by (wave, class)
+    std::vector<int64_t> item_off;               // [n_waves * K2J_NCLASS + 1]
+    std::vector<int32_t> jplots;                 // plot ids, grouped by structure operand
+};
+
 struct Handle {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
     std::string err;
     int64_t hit_budget = 0;          // bytes; 0 = default
     int64_t default_hit_budget = (int64_t)6 << 30;
-    int k2_ctas_per_sm = 0;          // persistent-grid size of kernel 2 = this x SM count; 0 = occupancy
+    int k2_ctas_per_sm = 0;          // persistent-grid size of the tile kernel = this x SM count; 0 = occupancy
     int k2_occupancy[K2_NVARIANT] = {0, 0, 0, 0, 0};
-    int tile_variant = 4;            // k2 inner-loop variant (k2_variant_*), fixed at upload
+    int tile_variant = 4;            // inner-loop variant of the tile kernel (k2_variant_*), fixed at upload
     int plan_variant = 4;            // variant the resident plan's strips were cut for
+    int k2_mode = 1;                 // 0 = all-pairs tile kernel (k2_tile.cuh), 1 = join kernel (k2_join.cuh)
+    int plan_mode = 1;               // mode the resident plan was made for
+    int plan_threads = 0;            // host threads for planning (0 = auto)
 
     // plan (host)
     std::vector<Operand> ops;
@@ -79,24 +97,33 @@ struct Handle {
     std::vector<Wave> waves;
     std::vector<int32_t> class_ids;              // task ids grouped by (wave, class)
     std::vector<int64_t> class_off;              // [n_waves*K3_NCLASS+1]
+    std::vector<TabChunk> chunks;                // join mode: table chunks of all structure-side operands
+    JoinPlan jp;
+    int64_t table_bytes = 0;
     int max_nb = 0;
     int64_t n_task = 0, n_sv = 0, n_seq = 0, seq_total = 0;
     int64_t hash_elems = 0, code_bytes = 0, max_wave_hits = 0;
     bool resident = false, ran = false;
     vapor_timings_t tm{};
     int64_t tm_padded_cells = 0;     // cells the tile kernel evaluates including strip padding
+    std::map<int32_t, int64_t> ovf_loc;   // plots whose hit list sits in d_ovf_hits after the last run: plot -> element offset
 
     // device
-    DevBuf<uint8_t> d_seq, d_code, d_task_status, d_sv_gt;
+    DevBuf<uint8_t> d_seq, d_code, d_task_status, d_sv_gt, d_table;
     DevBuf<Operand> d_ops;
     DevBuf<Plot> d_plots;
     DevBuf<Task> d_tasks;
-    DevBuf<int32_t> d_chunk_prefix, d_op_status, d_class_ids, d_sv_nscore;
-    DevBuf<int64_t> d_strip_prefix, d_sv_off, d_ovf_prefix;
-    DevBuf<uint32_t> d_hash, d_cnt, d_task_hits, d_gscratch, d_misc, d_qc;
+    DevBuf<TabChunk> d_chunks;
+    DevBuf<JoinItem> d_items;
+    DevBuf<int32_t> d_chunk_prefix, d_op_status, d_class_ids, d_sv_nscore, d_jplots;
+    DevBuf<int64_t> d_strip_prefix, d_sv_off;
+    DevBuf<uint32_t> d_hash, d_cnt, d_task_hits, d_gscratch, d_ovf_flags, d_qc;
     DevBuf<uint2> d_hits, d_ovf_hits;
     DevBuf<double> d_task_score, d_task_stat, d_pos, d_sv_qs, d_sv_gs, d_sv_gq;
-    DevBuf<unsigned long long> d_task_hitsum, d_queue;
+    DevBuf<unsigned long long> d_task_hitsum, d_queue, d_stats;
+    unsigned long long* h_stats = nullptr;       // pinned: [0] hits, [1] evaluated cells
+    uint32_t* h_flags = nullptr;                 // pinned: overflow flag per wave
+    size_t h_flags_cap = 0;
 
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     size_t ev_used = 0;
@@ -104,7 +131,7 @@ struct Handle {
     std::vector<Span> spans;
 };
 
-enum { CAT_H2D = 0, CAT_PACK, CAT_TILE, CAT_SCORE, CAT_GENO, CAT_D2H, CAT_N };
+enum { CAT_H2D = 0, CAT_PACK, CAT_TABLE, CAT_TILE, CAT_SCORE, CAT_GENO, CAT_D2H, CAT_N };
 
 int span_begin(Handle* h, int cat) {
     if (h->ev_used == h->ev_pool.size()) {
@@ -171,6 +198,81 @@ int k3_class_of(int nb) {
 // ------------------------------------------------------------------------------------------
 // planning: operands (k-mer word arrays), plots, tasks, waves
 // ------------------------------------------------------------------------------------------
+
+// Table chunks of every structure-side operand (join kernel).  op_chunk0[i] = first chunk of operand i, or -1.
+int64_t build_chunks(const std::vector<Operand>& ops, std::vector<TabChunk>& chunks, std::vector<int32_t>& op_chunk0) {
+    chunks.clear();
+    op_chunk0.assign(ops.size(), -1);
+    int64_t off = 0;
+    for (size_t i = 0; i < ops.size(); ++i) {
+        const Operand& o = ops[i];
+        if (!(o.flags & OPF_TABLE) || o.n <= 0) continue;
+        op_chunk0[i] = (int32_t)chunks.size();
+        for (int p0 = 0; p0 < o.n; p0 += K2J_CH) {
+            TabChunk c{};
+            c.op = (int32_t)i; c.pos0 = p0; c.len = std::min(K2J_CH, o.n - p0); c.bits = k2j_bits(c.len);
+            c.blob_bytes = k2j_blob_bytes(c.len, c.bits); c.blob_off = off;
+            off += c.blob_bytes;
+            chunks.push_back(c);
+        }
+    }
+    return off;
+}
+
+int k2j_class_of(int blob_bytes) {
+    for (int c = 0; c < K2J_NCLASS - 1; ++c) if (blob_bytes <= k2j_class_cap[c]) return c;
+    return K2J_NCLASS - 1;
+}
+
+// Items of the join kernel for every wave (= contiguous plot range): the wave's plots grouped by structure operand,
+// every group cut into runs of K2J_PLOTS_PER_ITEM plots, one item per (table chunk of the operand, run).
+void build_join_items(const std::vector<Plot>& plots, const std::vector<Wave>& waves, const std::vector<TabChunk>& chunks,
+                      const std::vector<int32_t>& op_chunk0, JoinPlan& jp)
+{
+    jp.items.clear(); jp.jplots.clear();
+    jp.item_off.assign(waves.size() * K2J_NCLASS + 1, 0);
+    jp.jplots.reserve(plots.size());
+    std::vector<int32_t> count, sorted;
+    std::vector<JoinItem> cls[K2J_NCLASS];
+    for (size_t wi = 0; wi < waves.size(); ++wi) {
+        const int64_t pb = waves[wi].plot_begin, pe = waves[wi].plot_end;
+        int32_t lo = INT32_MAX, hi = -1;
+        for (int64_t i = pb; i < pe; ++i) {
+            const Plot& p = plots[i];
+            if (p.n <= 0 || p.m <= 0) continue;
+            lo = std::min(lo, p.struct_op); hi = std::max(hi, p.struct_op);
+        }
+        for (auto& v : cls) v.clear();
+        if (hi >= lo) {
+            // counting sort of the wave's non-empty plots by structure operand (stable: task order inside a group)
+            count.assign((size_t)(hi - lo) + 2, 0);
+            for (int64_t i = pb; i < pe; ++i) { const Plot& p = plots[i]; if (p.n > 0 && p.m > 0) ++count[p.struct_op - lo + 1]; }
+            for (size_t q = 1; q < count.size(); ++q) count[q] += count[q - 1];
+            const int32_t total = count.back();
+            sorted.resize((size_t)total);
+            {
+                std::vector<int32_t> cur(count.begin(), count.end() - 1);
+                for (int64_t i = pb; i < pe; ++i) { const Plot& p = plots[i]; if (p.n > 0 && p.m > 0) sorted[cur[p.struct_op - lo]++] = (int32_t)i; }
+            }
+            for (int32_t op = lo; op <= hi; ++op) {
+                const int32_t g0 = count[op - lo], g1 = count[op - lo + 1];
+                if (g1 == g0 || op_chunk0[op] < 0) continue;
+                const int32_t jbase = (int32_t)jp.jplots.size();
+                jp.jplots.insert(jp.jplots.end(), sorted.begin() + g0, sorted.begin() + g1);
+                for (int32_t c = op_chunk0[op]; c < (int32_t)chunks.size() && chunks[c].op == op; ++c) {
+                    const int k = k2j_class_of(chunks[c].blob_bytes);
+                    for (int32_t a = 0; a < g1 - g0; a += K2J_PLOTS_PER_ITEM)
+                        cls[k].push_back(JoinItem{c, jbase + a, jbase + std::min<int32_t>(a + K2J_PLOTS_PER_ITEM, g1 - g0), 0});
+                }
+            }
+        }
+        for (int k = 0; k < K2J_NCLASS; ++k) {
+            jp.items.insert(jp.items.end(), cls[k].begin(), cls[k].end());
+            jp.item_off[wi * K2J_NCLASS + k + 1] = (int64_t)jp.items.size();
+        }
+    }
+}
+
 int plan_batch(Handle* h, const vapor_batch_t* in) {
     if (!in || !in->seq_off || (!in->seq_bytes && in->n_seq > 0 && in->seq_off[in->n_seq] > 0)) { h->err = "NULL batch arrays"; return VAPOR_E_ARG; }
     if (in->n_task > 0 && (!in->task_read || !in->task_ref || !in->task_alt || !in->task_miss || !in->task_k || !in->task_mode)) {
@@ -183,6 +285,8 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
         if (L < 0 || L >= (1ll << 27)) { h->err = "sequence length out of range (0 .. 2^27)"; return VAPOR_E_ARG; }
     }
     if (n_sv > 0 && (in->sv_task_off[0] != 0 || in->sv_task_off[n_sv] != n_task)) { h->err = "sv_task_off must cover [0, n_task]"; return VAPOR_E_ARG; }
+    for (int64_t s = 0; s < n_sv; ++s)
+        if (in->sv_task_off[s + 1] < in->sv_task_off[s]) { h->err = "sv_task_off must be non-decreasing"; return VAPOR_E_ARG; }
 
     h->ops.clear(); h->plots.clear(); h->tasks.clear(); h->waves.clear();
     h->tasks.reserve(n_task);
@@ -226,15 +330,19 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
         local.push_back({seq, k, flags, id});
         return id;
     };
-    auto add_plot = [&](int32_t rop, int32_t sop, int32_t miss) -> int32_t {
+    auto add_plot = [&](int32_t rop, int32_t sop, int32_t miss_bp) -> int32_t {
         const Operand& r = h->ops[rop];
-        const Operand& s = h->ops[sop];
+        Operand& s = h->ops[sop];
+        // the reference slices ref_seq[miss_bp:] (Simple_function.pyx:185-186): a negative miss_bp, which
+        // cigar2alignstart_by_pos can return, counts from the end of the string as Python slicing does
+        const int32_t miss = miss_bp >= 0 ? miss_bp : std::max(0, s.len + miss_bp);
         Plot p{};
         p.read_op = rop; p.struct_op = sop; p.miss = miss;
         p.n = r.n;
         p.m = (miss <= s.len) ? std::max(0, s.len - miss - s.k + 1) : 0;
         p.cap = (p.n > 0 && p.m > 0) ? (uint32_t)align4((int64_t)p.n + p.m + 32) : 0u;
         p.hit_off = 0;
+        s.flags |= OPF_TABLE;
         cells += (int64_t)p.n * p.m;
         h->plots.push_back(p);
         return (int32_t)h->plots.size() - 1;
@@ -253,7 +361,6 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
         if (rs < 0 || rs >= n_seq || fs < 0 || fs >= n_seq || as < 0 || as >= n_seq) { h->err = "task sequence index out of range"; return VAPOR_E_ARG; }
         if (k < 1 || k > K1_MAXK) { h->err = "window_size k must be 1..40"; return VAPOR_E_ARG; }
         if (mode < 0 || mode > 3) { h->err = "unknown mode"; return VAPOR_E_ARG; }
-        if (miss < 0) { h->err = "miss_bp must be >= 0"; return VAPOR_E_ARG; }
         Task tk{};
         tk.mode = mode;
         tk.len_ref = (int32_t)(in->seq_off[fs + 1] - in->seq_off[fs]);
@@ -280,17 +387,12 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
         h->chunk_prefix[i + 1] = h->chunk_prefix[i] + chunks;
         bases += h->ops[i].len;
     }
-    // strips + waves (plots were created in task order, so each wave is a contiguous plot range)
+    // waves (plots were created in task order, so each wave is a contiguous plot range)
     // hit slab of one wave: a quarter of the device memory free at open(), at most 24 GB, unless the caller set it
     const int64_t budget_bytes = h->hit_budget > 0 ? h->hit_budget : h->default_hit_budget;
     const int64_t budget_elems = std::max<int64_t>(budget_bytes / (int64_t)sizeof(uint2), 1 << 16);
-    h->strip_prefix.assign(h->plots.size() + 1, 0);
     h->plan_variant = h->tile_variant;
-    int64_t padded_cells = 0;
-    for (size_t i = 0; i < h->plots.size(); ++i) {
-        h->strip_prefix[i + 1] = h->strip_prefix[i] + cut_strips(h->plots[i], k2_variant_rows(h->plan_variant), &padded_cells);
-    }
-    h->tm_padded_cells = padded_cells;
+    h->plan_mode = h->k2_mode;
     h->max_nb = 1; h->max_wave_hits = 0;
     {
         Wave w{0, 0, 0, 0, 0};
@@ -315,6 +417,19 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
         }
         if (w.task_end > w.task_begin) h->waves.push_back(w);
     }
+    // kernel-2 plan: strips of the tile kernel, or tables + items of the join kernel
+    int64_t padded_cells = 0;
+    h->strip_prefix.assign(h->plots.size() + 1, 0);
+    h->chunks.clear(); h->jp = JoinPlan{}; h->table_bytes = 0;
+    if (h->plan_mode == 0) {
+        for (size_t i = 0; i < h->plots.size(); ++i)
+            h->strip_prefix[i + 1] = h->strip_prefix[i] + cut_strips(h->plots[i], k2_variant_rows(h->plan_variant), &padded_cells);
+    } else {
+        std::vector<int32_t> op_chunk0;
+        h->table_bytes = build_chunks(h->ops, h->chunks, op_chunk0);
+        build_join_items(h->plots, h->waves, h->chunks, op_chunk0, h->jp);
+    }
+    h->tm_padded_cells = padded_cells;
     // kernel-3 classes per wave
     h->class_ids.resize(n_task);
     h->class_off.assign(h->waves.size() * K3_NCLASS + 1, 0);
@@ -353,7 +468,18 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
     h->tm = vapor_timings_t{};
     h->tm.cells = cells; h->tm.n_plots = (int64_t)h->plots.size(); h->tm.n_operands = (int64_t)h->ops.size();
     h->tm.padded_cells = h->tm_padded_cells;
-    h->tm.n_strips = h->strip_prefix.back(); h->tm.n_waves = (int64_t)h->waves.size(); h->tm.bases = bases;
+    h->tm.n_strips = h->plan_mode == 0 ? h->strip_prefix.back() : (int64_t)h->jp.items.size();
+    h->tm.n_waves = (int64_t)h->waves.size(); h->tm.bases = bases;
+    h->tm.k2_mode = h->plan_mode;
+    return VAPOR_OK;
+}
+
+int ensure_flags(Handle* h, size_t n) {
+    if (n <= h->h_flags_cap) return VAPOR_OK;
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    h->h_flags = nullptr; h->h_flags_cap = 0;
+    CK(cudaMallocHost(&h->h_flags, (n + 64) * sizeof(uint32_t)));
+    h->h_flags_cap = n + 64;
     return VAPOR_OK;
 }
 
@@ -380,7 +506,6 @@ int upload_impl(Handle* h, const vapor_batch_t* in) {
     CK(h->d_plots.ensure(h->plots.size() + 1));
     CK(h->d_tasks.ensure(nt + 1));
     CK(h->d_chunk_prefix.ensure(h->chunk_prefix.size()));
-    CK(h->d_strip_prefix.ensure(h->strip_prefix.size()));
     CK(h->d_class_ids.ensure(nt + 1));
     CK(h->d_sv_off.ensure(nsv + 1));
     CK(h->d_hash.ensure((size_t)h->hash_elems));
@@ -393,9 +518,16 @@ int upload_impl(Handle* h, const vapor_batch_t* in) {
     CK(h->d_pos.ensure(nt + 1));
     CK(h->d_sv_qs.ensure(nsv + 1)); CK(h->d_sv_gs.ensure(nsv + 1)); CK(h->d_sv_gq.ensure(nsv + 1));
     CK(h->d_sv_gt.ensure(nsv + 1)); CK(h->d_sv_nscore.ensure(nsv + 1));
-    CK(h->d_queue.ensure(4)); CK(h->d_misc.ensure(16));
+    CK(h->d_queue.ensure(4)); CK(h->d_stats.ensure(4)); CK(h->d_ovf_flags.ensure(h->waves.size() + 1));
+    { int rcf = ensure_flags(h, h->waves.size() + 1); if (rcf) return rcf; }
     if (k3_class_of(h->max_nb) == K3_NCLASS - 1)
         CK(h->d_gscratch.ensure((size_t)2 * h->sm_count * k3_scratch_words(h->max_nb)));
+    if (h->plan_mode == 0) {
+        CK(h->d_strip_prefix.ensure(h->strip_prefix.size()));
+    } else {
+        CK(h->d_chunks.ensure(h->chunks.size() + 1)); CK(h->d_items.ensure(h->jp.items.size() + 1));
+        CK(h->d_jplots.ensure(h->jp.jplots.size() + 1)); CK(h->d_table.ensure((size_t)h->table_bytes + 64));
+    }
 
     if (sp < 0) {
         sp = span_begin(h, CAT_H2D);
@@ -405,8 +537,14 @@ int upload_impl(Handle* h, const vapor_batch_t* in) {
     CK(cudaMemcpyAsync(h->d_plots.p, h->plots.data(), h->plots.size() * sizeof(Plot), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_tasks.p, h->tasks.data(), nt * sizeof(Task), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_chunk_prefix.p, h->chunk_prefix.data(), h->chunk_prefix.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_strip_prefix.p, h->strip_prefix.data(), h->strip_prefix.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_class_ids.p, h->class_ids.data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (h->plan_mode == 0) {
+        CK(cudaMemcpyAsync(h->d_strip_prefix.p, h->strip_prefix.data(), h->strip_prefix.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        CK(cudaMemcpyAsync(h->d_chunks.p, h->chunks.data(), h->chunks.size() * sizeof(TabChunk), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_items.p, h->jp.items.data(), h->jp.items.size() * sizeof(JoinItem), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_jplots.p, h->jp.jplots.data(), h->jp.jplots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    }
     if (nsv) CK(cudaMemcpyAsync(h->d_sv_off.p, in->sv_task_off, (nsv + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     span_end(h, sp);
     CK(cudaStreamSynchronize(h->stream));
@@ -434,8 +572,8 @@ void launch_k2_variant(Handle* h, const K2Params& kp) {
     const int grid = (int)std::min<int64_t>((kp.n_strips + K2_WARPS - 1) / K2_WARPS, (int64_t)h->sm_count * per_sm);
     kern<<<grid, K2_THREADS, 0, h->stream>>>(kp);
 }
-void launch_k2(Handle* h, const K2Params& kp) {
-    switch (h->plan_variant) {
+void launch_k2(Handle* h, const K2Params& kp, int variant) {
+    switch (variant) {
         case 0:  launch_k2_variant<0>(h, kp); break;
         case 2:  launch_k2_variant<2>(h, kp); break;
         case 3:  launch_k2_variant<3>(h, kp); break;
@@ -444,164 +582,279 @@ void launch_k2(Handle* h, const K2Params& kp) {
     }
 }
 
+// the join kernel over the items [o0, o1) of every class of one wave; returns the launches made
+int launch_k2_join(Handle* h, const JoinPlan& jp, size_t wi, K2JParams kp) {
+    int launches = 0;
+    const JoinItem* items0 = kp.items;
+    for (int c = 0; c < K2J_NCLASS; ++c) {
+        const int64_t o0 = jp.item_off[wi * K2J_NCLASS + c], o1 = jp.item_off[wi * K2J_NCLASS + c + 1];
+        if (o1 == o0) continue;
+        kp.items = items0 + o0;
+        k2_join_match<<<(unsigned)(o1 - o0), K2J_THREADS, (size_t)k2j_class_cap[c], h->stream>>>(kp);
+        ++launches;
+    }
+    return launches;
+}
+
+// kernel 3 over task ids [o0, o1) of scratch class c
+void launch_k3_class(Handle* h, K3Params kp, int c, int max_nb) {
+    if (c < K3_NCLASS - 1) {
+        kp.nb_cap = k3_class_cap[c]; kp.use_global = 0; kp.gscratch = nullptr;
+        const size_t smem = k3_scratch_words(kp.nb_cap) * sizeof(uint32_t);
+        k3_score_reads<<<kp.n_ids, K3_THREADS, smem, h->stream>>>(kp);
+    } else {
+        kp.nb_cap = max_nb; kp.use_global = 1; kp.gscratch = h->d_gscratch.p;
+        const int grid = std::min(kp.n_ids, 2 * h->sm_count);
+        k3_score_reads<<<grid, K3_THREADS, 0, h->stream>>>(kp);
+    }
+}
+
+__global__ void k_sum_counts(const uint32_t* __restrict__ cnt, long long n, unsigned long long* out) {
+    unsigned long long s = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += cnt[i];
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+// A wave whose first pass overflowed some hit lists (repeats: more dots than n + m + 32): the tasks that own such a
+// plot are scored again from copies of their plots with exact capacities in d_ovf_hits.  The resident plan
+// (h->plots / d_plots) is never modified, so a later run() on the same batch starts from the same state.
+int redo_wave(Handle* h, size_t wi, int64_t* launches) {
+    const Wave& w = h->waves[wi];
+    const int n_plots = (int)(w.plot_end - w.plot_begin);
+    std::vector<uint32_t> cnt_host((size_t)n_plots);
+    CK(cudaMemcpy(cnt_host.data(), h->d_cnt.p + w.plot_begin, n_plots * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> remap((size_t)n_plots, -1);
+    std::vector<Plot> re_plots; std::vector<Task> re_tasks; std::vector<int32_t> re_out; std::vector<int64_t> re_prefix{0};
+    const int rows = k2_variant_rows(h->tile_variant);
+    int64_t extra = 0;
+    h->ovf_loc.clear();
+    for (int64_t t = w.task_begin; t < w.task_end; ++t) {
+        const Task& tk = h->tasks[t];
+        bool over = false;
+        for (int i = 0; i < 4; ++i) if (tk.plot[i] >= 0) {
+            const Plot& p = h->plots[tk.plot[i]];
+            if (cnt_host[tk.plot[i] - w.plot_begin] > p.cap) over = true;
+        }
+        if (!over) continue;
+        Task nt = tk;
+        for (int i = 0; i < 4; ++i) if (tk.plot[i] >= 0) {
+            const int32_t li = (int32_t)(tk.plot[i] - w.plot_begin);
+            if (remap[li] < 0) {
+                Plot p = h->plots[tk.plot[i]];
+                if (cnt_host[li] > (1u << 30)) { h->err = "a plot produced more than 2^30 hits"; return VAPOR_E_CAPACITY; }
+                p.cap = (uint32_t)align4(std::max<uint32_t>(cnt_host[li], 4u));
+                p.hit_off = extra;
+                h->ovf_loc[tk.plot[i]] = extra;
+                extra += p.cap;
+                re_prefix.push_back(re_prefix.back() + cut_strips(p, rows, nullptr));
+                remap[li] = (int32_t)re_plots.size();
+                re_plots.push_back(p);
+            }
+            nt.plot[i] = remap[li];
+        }
+        re_tasks.push_back(nt);
+        re_out.push_back((int32_t)t);
+    }
+    h->tm.n_overflow_plots += (int64_t)re_plots.size();
+    if (re_tasks.empty()) return VAPOR_OK;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if ((size_t)extra * sizeof(uint2) + ((size_t)1 << 30) > free_b + h->d_ovf_hits.cap * sizeof(uint2)) {
+        h->err = "hit lists of repetitive plots exceed device memory"; return VAPOR_E_CAPACITY;
+    }
+    CK(h->d_ovf_hits.ensure((size_t)extra + 64));
+    // group the re-scored tasks by kernel-3 scratch class
+    std::vector<int32_t> ids[K3_NCLASS];
+    int re_max_nb = 1;
+    for (size_t i = 0; i < re_tasks.size(); ++i) {
+        int nb = 1;
+        for (int q = 0; q < 4; ++q) if (re_tasks[i].plot[q] >= 0) { const Plot& p = re_plots[re_tasks[i].plot[q]]; nb = std::max(nb, p.n + p.m - 1); }
+        ids[k3_class_of(nb)].push_back((int32_t)i);
+        re_max_nb = std::max(re_max_nb, nb);
+    }
+    std::vector<int32_t> id_flat, out_flat; int64_t id_off[K3_NCLASS + 1] = {0};
+    for (int c = 0; c < K3_NCLASS; ++c) {
+        for (int32_t i : ids[c]) { id_flat.push_back(i); out_flat.push_back(re_out[i]); }
+        id_off[c + 1] = (int64_t)id_flat.size();
+    }
+    DevBuf<Plot> d_re; DevBuf<Task> d_rt; DevBuf<uint32_t> d_recnt, d_reflag; DevBuf<int64_t> d_repre; DevBuf<int32_t> d_ids, d_out;
+    int rc = VAPOR_OK;
+    auto cleanup = [&]() { d_re.release(); d_rt.release(); d_recnt.release(); d_reflag.release(); d_repre.release(); d_ids.release(); d_out.release(); };
+    #define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); return VAPOR_E_CUDA; } } while (0)
+    CKR(d_re.ensure(re_plots.size())); CKR(d_rt.ensure(re_tasks.size())); CKR(d_recnt.ensure(re_plots.size())); CKR(d_reflag.ensure(4));
+    CKR(d_repre.ensure(re_prefix.size())); CKR(d_ids.ensure(id_flat.size())); CKR(d_out.ensure(out_flat.size()));
+    if (k3_class_of(re_max_nb) == K3_NCLASS - 1) CKR(h->d_gscratch.ensure((size_t)2 * h->sm_count * k3_scratch_words(std::max(re_max_nb, h->max_nb))));
+    CKR(cudaMemcpyAsync(d_re.p, re_plots.data(), re_plots.size() * sizeof(Plot), cudaMemcpyHostToDevice, h->stream));
+    CKR(cudaMemcpyAsync(d_rt.p, re_tasks.data(), re_tasks.size() * sizeof(Task), cudaMemcpyHostToDevice, h->stream));
+    CKR(cudaMemcpyAsync(d_repre.p, re_prefix.data(), re_prefix.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CKR(cudaMemcpyAsync(d_ids.p, id_flat.data(), id_flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CKR(cudaMemcpyAsync(d_out.p, out_flat.data(), out_flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CKR(cudaMemsetAsync(d_recnt.p, 0, re_plots.size() * sizeof(uint32_t), h->stream));
+    CKR(cudaMemsetAsync(d_reflag.p, 0, 4 * sizeof(uint32_t), h->stream));
+    CKR(cudaMemsetAsync(h->d_queue.p, 0, 4 * sizeof(unsigned long long), h->stream));
+    int sp = span_begin(h, CAT_TILE);
+    if (re_prefix.back() > 0) {
+        K2Params kp{};
+        kp.plots = d_re.p; kp.ops = h->d_ops.p; kp.strip_prefix = d_repre.p;
+        kp.n_plots = (int)re_plots.size(); kp.n_strips = re_prefix.back(); kp.strip_base = 0;
+        kp.hash = h->d_hash.p; kp.code = h->d_code.p; kp.hits = h->d_ovf_hits.p;
+        kp.cnt = d_recnt.p; kp.queue = h->d_queue.p; kp.overflow = d_reflag.p;
+        launch_k2(h, kp, h->tile_variant);
+        ++*launches;
+    }
+    span_end(h, sp);
+    sp = span_begin(h, CAT_SCORE);
+    for (int c = 0; c < K3_NCLASS; ++c) {
+        if (id_off[c + 1] == id_off[c]) continue;
+        K3Params kp{};
+        kp.tasks = d_rt.p; kp.task_ids = d_ids.p + id_off[c]; kp.out_ids = d_out.p + id_off[c]; kp.n_ids = (int)(id_off[c + 1] - id_off[c]);
+        kp.plots = d_re.p; kp.cnt = d_recnt.p; kp.op_status = h->d_op_status.p; kp.hits = h->d_ovf_hits.p;
+        kp.task_score = h->d_task_score.p; kp.task_status = h->d_task_status.p; kp.task_stat = h->d_task_stat.p;
+        kp.task_hits = h->d_task_hits.p; kp.task_hitsum = h->d_task_hitsum.p;
+        launch_k3_class(h, kp, c, std::max(re_max_nb, h->max_nb));
+        ++*launches;
+    }
+    span_end(h, sp);
+    CKR(cudaGetLastError());
+    CKR(cudaStreamSynchronize(h->stream));
+    #undef CKR
+    cleanup();
+    return rc;
+}
+
 int run_impl(Handle* h) {
     if (!h->resident) { h->err = "no resident batch: call vapor_gpu_upload first"; return VAPOR_E_STATE; }
     CK(cudaSetDevice(h->device));
-    const size_t nt = (size_t)h->n_task, nsv = (size_t)h->n_sv;
+    const size_t nsv = (size_t)h->n_sv;
     int64_t launches = 0;
     h->tm.n_overflow_plots = 0;
-    cudaEvent_t ev_total0, ev_total1;
-    CK(cudaEventCreate(&ev_total0)); CK(cudaEventCreate(&ev_total1));
-    CK(cudaEventRecord(ev_total0, h->stream));
+    h->ovf_loc.clear();
+    h->spans.clear(); h->ev_used = 0;
+    CK(cudaEventRecord(h->ev_run0, h->stream));
 
-    // ---- kernel 1 -------------------------------------------------------------------------
+    // ---- kernel 1 (+ 1b: tables of the structure-side operands) ---------------------------------
     int sp = span_begin(h, CAT_PACK);
     CK(cudaMemsetAsync(h->d_op_status.p, 0, (h->ops.size() + 1) * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(h->d_cnt.p, 0, (h->plots.size() + 1) * sizeof(uint32_t), h->stream));
+    CK(cudaMemsetAsync(h->d_ovf_flags.p, 0, (h->waves.size() + 1) * sizeof(uint32_t), h->stream));
+    CK(cudaMemsetAsync(h->d_stats.p, 0, 4 * sizeof(unsigned long long), h->stream));
     if (!h->ops.empty()) {
         k1_pack_kmers<<<h->chunk_prefix.back(), K1_THREADS, 0, h->stream>>>(
             h->d_seq.p, h->d_ops.p, h->d_chunk_prefix.p, (int)h->ops.size(), h->d_hash.p, h->d_code.p, h->d_op_status.p);
         ++launches;
     }
     span_end(h, sp);
+    if (h->plan_mode == 1 && !h->chunks.empty()) {
+        sp = span_begin(h, CAT_TABLE);
+        k1b_build_tables<<<(unsigned)h->chunks.size(), K1B_THREADS, 0, h->stream>>>(h->d_chunks.p, h->d_ops.p, h->d_hash.p, h->d_table.p);
+        ++launches;
+        span_end(h, sp);
+    }
     CK(cudaGetLastError());
 
-    std::vector<uint32_t> cnt_host;
     for (size_t wi = 0; wi < h->waves.size(); ++wi) {
         const Wave& w = h->waves[wi];
-        const int n_plots = (int)(w.plot_end - w.plot_begin);
-        const int64_t sbase = h->strip_prefix[w.plot_begin];
-        const int64_t n_strips = h->strip_prefix[w.plot_end] - sbase;
         // ---- kernel 2 ---------------------------------------------------------------------
         sp = span_begin(h, CAT_TILE);
-        CK(cudaMemsetAsync(h->d_queue.p, 0, 4 * sizeof(unsigned long long), h->stream));
-        CK(cudaMemsetAsync(h->d_misc.p, 0, 16 * sizeof(uint32_t), h->stream));
-        if (n_strips > 0) {
-            K2Params kp{};
-            kp.plots = h->d_plots.p + w.plot_begin;
-            kp.ops = h->d_ops.p;
-            kp.strip_prefix = h->d_strip_prefix.p + w.plot_begin;
-            kp.n_plots = n_plots;
-            kp.n_strips = n_strips;
-            kp.strip_base = sbase;
-            kp.hash = h->d_hash.p; kp.code = h->d_code.p;
-            kp.hits = h->d_hits.p;
-            kp.cnt = h->d_cnt.p + w.plot_begin;
-            kp.queue = h->d_queue.p;
-            kp.overflow = h->d_misc.p;
-            launch_k2(h, kp);
-            ++launches;
+        if (h->plan_mode == 0) {
+            const int n_plots = (int)(w.plot_end - w.plot_begin);
+            const int64_t sbase = h->strip_prefix[w.plot_begin];
+            const int64_t n_strips = h->strip_prefix[w.plot_end] - sbase;
+            CK(cudaMemsetAsync(h->d_queue.p, 0, 4 * sizeof(unsigned long long), h->stream));
+            if (n_strips > 0) {
+                K2Params kp{};
+                kp.plots = h->d_plots.p + w.plot_begin;
+                kp.ops = h->d_ops.p;
+                kp.strip_prefix = h->d_strip_prefix.p + w.plot_begin;
+                kp.n_plots = n_plots;
+                kp.n_strips = n_strips;
+                kp.strip_base = sbase;
+                kp.hash = h->d_hash.p; kp.code = h->d_code.p;
+                kp.hits = h->d_hits.p;
+                kp.cnt = h->d_cnt.p + w.plot_begin;
+                kp.queue = h->d_queue.p;
+                kp.overflow = h->d_ovf_flags.p + wi;
+                launch_k2(h, kp, h->plan_variant);
+                ++launches;
+            }
+        } else {
+            K2JParams kp{};
+            kp.items = h->d_items.p; kp.jplots = h->d_jplots.p; kp.chunks = h->d_chunks.p; kp.plots = h->d_plots.p;
+            kp.ops = h->d_ops.p; kp.hash = h->d_hash.p; kp.code = h->d_code.p; kp.table = h->d_table.p;
+            kp.hits = h->d_hits.p; kp.cnt = h->d_cnt.p; kp.overflow = h->d_ovf_flags.p + wi; kp.qc = nullptr;
+            kp.evaluated = h->d_stats.p + 1;
+            launches += launch_k2_join(h, h->jp, wi, kp);
         }
         span_end(h, sp);
         CK(cudaGetLastError());
-        // ---- overflow check: plots that found more hits than their first-pass capacity --------
-        uint32_t ovf = 0;
-        CK(cudaMemcpyAsync(&ovf, h->d_misc.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        if (ovf) {
-            cnt_host.resize(n_plots);
-            CK(cudaMemcpy(cnt_host.data(), h->d_cnt.p + w.plot_begin, n_plots * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-            std::vector<Plot> re_plots; std::vector<int64_t> re_prefix{0}; std::vector<int32_t> re_ids;
-            int64_t extra = 0;
-            for (int i = 0; i < n_plots; ++i) {
-                Plot& p = h->plots[w.plot_begin + i];
-                if (cnt_host[i] > p.cap) {
-                    if (cnt_host[i] > (1u << 30)) { h->err = "a plot produced more than 2^30 hits"; return VAPOR_E_CAPACITY; }
-                    p.cap = (uint32_t)align4(cnt_host[i]);
-                    p.hit_off = extra;                       // relative to the overflow buffer
-                    extra += p.cap;
-                    re_plots.push_back(p); re_ids.push_back(i);
-                    re_prefix.push_back(re_prefix.back() + (h->strip_prefix[w.plot_begin + i + 1] - h->strip_prefix[w.plot_begin + i]));
-                }
-            }
-            h->tm.n_overflow_plots += (int64_t)re_plots.size();
-            size_t free_b = 0, total_b = 0;
-            cudaMemGetInfo(&free_b, &total_b);
-            if ((size_t)extra * sizeof(uint2) + ((size_t)1 << 30) > free_b + h->d_ovf_hits.cap * sizeof(uint2)) {
-                h->err = "hit lists of repetitive plots exceed device memory"; return VAPOR_E_CAPACITY;
-            }
-            CK(h->d_ovf_hits.ensure((size_t)extra + 64));
-            // express overflow hit offsets relative to d_hits so kernel 3 needs one base pointer
-            const int64_t delta = (int64_t)(h->d_ovf_hits.p - h->d_hits.p);
-            DevBuf<Plot> d_re; DevBuf<uint32_t> d_recnt;
-            CK(d_re.ensure(re_plots.size())); CK(d_recnt.ensure(re_plots.size()));
-            CK(h->d_ovf_prefix.ensure(re_prefix.size()));
-            for (size_t i = 0; i < re_plots.size(); ++i) {
-                re_plots[i].hit_off += delta;
-                h->plots[w.plot_begin + re_ids[i]].hit_off = re_plots[i].hit_off;
-            }
-            CK(cudaMemcpy(d_re.p, re_plots.data(), re_plots.size() * sizeof(Plot), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(h->d_ovf_prefix.p, re_prefix.data(), re_prefix.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(h->d_plots.p + w.plot_begin, &h->plots[w.plot_begin], n_plots * sizeof(Plot), cudaMemcpyHostToDevice));
-            CK(cudaMemset(d_recnt.p, 0, re_plots.size() * sizeof(uint32_t)));
-            CK(cudaMemsetAsync(h->d_queue.p, 0, 4 * sizeof(unsigned long long), h->stream));
-            CK(cudaMemsetAsync(h->d_misc.p, 0, 16 * sizeof(uint32_t), h->stream));
-            sp = span_begin(h, CAT_TILE);
-            K2Params kp{};
-            kp.plots = d_re.p; kp.ops = h->d_ops.p; kp.strip_prefix = h->d_ovf_prefix.p;
-            kp.n_plots = (int)re_plots.size(); kp.n_strips = re_prefix.back(); kp.strip_base = 0;
-            kp.hash = h->d_hash.p; kp.code = h->d_code.p; kp.hits = h->d_hits.p;
-            kp.cnt = d_recnt.p; kp.queue = h->d_queue.p; kp.overflow = h->d_misc.p;
-            launch_k2(h, kp);
-            ++launches;
-            span_end(h, sp);
-            CK(cudaGetLastError());
-            CK(cudaStreamSynchronize(h->stream));
-            d_re.release(); d_recnt.release();
-        }
         // ---- kernel 3, one launch per scratch class ----------------------------------------------
         sp = span_begin(h, CAT_SCORE);
         for (int c = 0; c < K3_NCLASS; ++c) {
             const int64_t o0 = h->class_off[wi * K3_NCLASS + c], o1 = h->class_off[wi * K3_NCLASS + c + 1];
             if (o1 == o0) continue;
             K3Params kp{};
-            kp.tasks = h->d_tasks.p; kp.task_ids = h->d_class_ids.p + o0; kp.n_ids = (int)(o1 - o0);
+            kp.tasks = h->d_tasks.p; kp.task_ids = h->d_class_ids.p + o0; kp.out_ids = nullptr; kp.n_ids = (int)(o1 - o0);
             kp.plots = h->d_plots.p; kp.cnt = h->d_cnt.p; kp.op_status = h->d_op_status.p;
             kp.hits = h->d_hits.p;
             kp.task_score = h->d_task_score.p; kp.task_status = h->d_task_status.p; kp.task_stat = h->d_task_stat.p;
             kp.task_hits = h->d_task_hits.p; kp.task_hitsum = h->d_task_hitsum.p;
-            if (c < K3_NCLASS - 1) {
-                kp.nb_cap = k3_class_cap[c]; kp.use_global = 0; kp.gscratch = nullptr;
-                const size_t smem = k3_scratch_words(kp.nb_cap) * sizeof(uint32_t);
-                k3_score_reads<<<kp.n_ids, K3_THREADS, smem, h->stream>>>(kp);
-            } else {
-                kp.nb_cap = h->max_nb; kp.use_global = 1; kp.gscratch = h->d_gscratch.p;
-                const int grid = std::min(kp.n_ids, 2 * h->sm_count);
-                k3_score_reads<<<grid, K3_THREADS, 0, h->stream>>>(kp);
-            }
+            launch_k3_class(h, kp, c, h->max_nb);
             ++launches;
         }
         span_end(h, sp);
         CK(cudaGetLastError());
     }
     // ---- kernel 4 -------------------------------------------------------------------------
-    sp = span_begin(h, CAT_GENO);
-    if (nsv) {
-        k4_genotype<<<(unsigned)((nsv + 127) / 128), 128, 0, h->stream>>>(
-            h->d_sv_off.p, (int)nsv, h->d_task_score.p, h->d_task_status.p, h->d_pos.p,
-            h->d_sv_qs.p, h->d_sv_gs.p, h->d_sv_gq.p, h->d_sv_gt.p, h->d_sv_nscore.p);
+    auto genotype = [&]() -> int {
+        int s4 = span_begin(h, CAT_GENO);
+        if (nsv) {
+            k4_genotype<<<(unsigned)((nsv + 127) / 128), 128, 0, h->stream>>>(
+                h->d_sv_off.p, (int)nsv, h->d_task_score.p, h->d_task_status.p, h->d_pos.p,
+                h->d_sv_qs.p, h->d_sv_gs.p, h->d_sv_gq.p, h->d_sv_gt.p, h->d_sv_nscore.p);
+            ++launches;
+        }
+        span_end(h, s4);
+        CK(cudaGetLastError());
+        return VAPOR_OK;
+    };
+    { int rc = genotype(); if (rc) return rc; }
+    if (!h->plots.empty()) {
+        k_sum_counts<<<std::min<int64_t>(((int64_t)h->plots.size() + 255) / 256, 4 * h->sm_count), 256, 0, h->stream>>>(
+            h->d_cnt.p, (long long)h->plots.size(), h->d_stats.p);
         ++launches;
     }
-    span_end(h, sp);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ev_total1, h->stream));
+    CK(cudaEventRecord(h->ev_run1, h->stream));
+    // one host round trip per run: overflow flags of all waves + the run's counters
+    CK(cudaMemcpyAsync(h->h_flags, h->d_ovf_flags.p, (h->waves.size() + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_stats, h->d_stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     float acc[CAT_N] = {0};
     collect_spans(h, acc);
-    h->tm.pack_ms = acc[CAT_PACK]; h->tm.tile_ms = acc[CAT_TILE]; h->tm.score_ms = acc[CAT_SCORE]; h->tm.genotype_ms = acc[CAT_GENO];
-    float tot = 0; cudaEventElapsedTime(&tot, ev_total0, ev_total1);
-    h->tm.total_ms = tot;
-    cudaEventDestroy(ev_total0); cudaEventDestroy(ev_total1);
-    h->tm.launches = launches;
-    // total hits
-    {
-        std::vector<uint32_t> c(h->plots.size());
-        if (!c.empty()) CK(cudaMemcpy(c.data(), h->d_cnt.p, c.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        int64_t tot_hits = 0;
-        for (auto v : c) tot_hits += v;
-        h->tm.hits = tot_hits;
+    float tot = 0; cudaEventElapsedTime(&tot, h->ev_run0, h->ev_run1);
+    bool any_ovf = false;
+    for (size_t wi = 0; wi < h->waves.size(); ++wi) any_ovf |= h->h_flags[wi] != 0;
+    if (any_ovf) {                                   // rare: repeats.  Re-score the affected tasks, then the summaries again
+        CK(cudaEventRecord(h->ev_run0, h->stream));
+        for (size_t wi = 0; wi < h->waves.size(); ++wi) {
+            if (!h->h_flags[wi]) continue;
+            int rc = redo_wave(h, wi, &launches);
+            if (rc) { h->spans.clear(); h->ev_used = 0; return rc; }
+        }
+        { int rc = genotype(); if (rc) return rc; }
+        CK(cudaEventRecord(h->ev_run1, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        collect_spans(h, acc);
+        float t2 = 0; cudaEventElapsedTime(&t2, h->ev_run0, h->ev_run1);
+        tot += t2;
     }
-    (void)nt;
+    h->tm.pack_ms = acc[CAT_PACK]; h->tm.table_ms = acc[CAT_TABLE]; h->tm.tile_ms = acc[CAT_TILE];
+    h->tm.score_ms = acc[CAT_SCORE]; h->tm.genotype_ms = acc[CAT_GENO];
+    h->tm.total_ms = tot;
+    h->tm.launches = launches;
+    h->tm.hits = (int64_t)h->h_stats[0];
+    h->tm.evaluated_cells = h->plan_mode == 0 ? h->tm.padded_cells : (int64_t)h->h_stats[1];
     h->ran = true;
     return VAPOR_OK;
 }
@@ -780,7 +1033,12 @@ int vapor_gpu_open(int device, void** handle) {
     if (e != cudaSuccess) { g_open_error = std::string("kernel image not loadable on this device: ") + cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return VAPOR_E_CUDA; }
     e = cudaFuncSetAttribute(k3_score_reads, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(k3_scratch_words(k3_class_cap[K3_NCLASS - 2]) * sizeof(uint32_t)));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_join_match, cudaFuncAttributeMaxDynamicSharedMemorySize, k2j_class_cap[K2J_NCLASS - 1]);
     if (e != cudaSuccess) { g_open_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return VAPOR_E_CUDA; }
+    e = cudaEventCreate(&h->ev_run0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev_run1);
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_stats, 4 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { g_open_error = std::string("event / pinned allocation: ") + cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return VAPOR_E_CUDA; }
     *handle = h;
     return VAPOR_OK;
 }
@@ -790,14 +1048,18 @@ int vapor_gpu_close(void* handle) {
     Handle* h = static_cast<Handle*>(handle);
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    h->d_seq.release(); h->d_code.release(); h->d_task_status.release(); h->d_sv_gt.release();
-    h->d_ops.release(); h->d_plots.release(); h->d_tasks.release();
-    h->d_chunk_prefix.release(); h->d_op_status.release(); h->d_class_ids.release(); h->d_sv_nscore.release();
-    h->d_strip_prefix.release(); h->d_sv_off.release(); h->d_ovf_prefix.release();
-    h->d_hash.release(); h->d_cnt.release(); h->d_task_hits.release(); h->d_gscratch.release(); h->d_misc.release(); h->d_qc.release();
+    h->d_seq.release(); h->d_code.release(); h->d_task_status.release(); h->d_sv_gt.release(); h->d_table.release();
+    h->d_ops.release(); h->d_plots.release(); h->d_tasks.release(); h->d_chunks.release(); h->d_items.release();
+    h->d_chunk_prefix.release(); h->d_op_status.release(); h->d_class_ids.release(); h->d_sv_nscore.release(); h->d_jplots.release();
+    h->d_strip_prefix.release(); h->d_sv_off.release();
+    h->d_hash.release(); h->d_cnt.release(); h->d_task_hits.release(); h->d_gscratch.release(); h->d_ovf_flags.release(); h->d_qc.release();
     h->d_hits.release(); h->d_ovf_hits.release();
     h->d_task_score.release(); h->d_task_stat.release(); h->d_pos.release(); h->d_sv_qs.release(); h->d_sv_gs.release(); h->d_sv_gq.release();
-    h->d_task_hitsum.release(); h->d_queue.release();
+    h->d_task_hitsum.release(); h->d_queue.release(); h->d_stats.release();
+    if (h->h_stats) cudaFreeHost(h->h_stats);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->ev_run0) cudaEventDestroy(h->ev_run0);
+    if (h->ev_run1) cudaEventDestroy(h->ev_run1);
     for (auto& ev : h->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaStreamDestroy(h->stream);
     delete h;
@@ -819,6 +1081,15 @@ int vapor_gpu_set_option(void* handle, const char* name, int64_t value) {
         if (value < 0 || value >= K2_NVARIANT) { h->err = "tile_variant out of range"; return VAPOR_E_ARG; }
         h->tile_variant = (int)value; h->resident = false; h->ran = false;       // strips must be re-cut
         return VAPOR_OK;
+    }
+    if (n == "k2_mode") {
+        if (value < 0 || value > 1) { h->err = "k2_mode must be 0 (tile) or 1 (join)"; return VAPOR_E_ARG; }
+        h->k2_mode = (int)value; h->resident = false; h->ran = false;             // the kernel-2 plan must be rebuilt
+        return VAPOR_OK;
+    }
+    if (n == "plan_threads") {
+        if (value < 0 || value > 256) { h->err = "plan_threads out of range"; return VAPOR_E_ARG; }
+        h->plan_threads = (int)value; return VAPOR_OK;
     }
     if (n == "k2_ctas_per_sm") {
         if (value < 0 || value > 32) { h->err = "k2_ctas_per_sm out of range"; return VAPOR_E_ARG; }
@@ -888,7 +1159,9 @@ int vapor_gpu_dotdata(void* handle, int k, const uint8_t* read, int64_t read_len
     CK(cudaMemcpy(&cnt, h->d_cnt.p + h->tasks[0].plot[0], sizeof(uint32_t), cudaMemcpyDeviceToHost));
     *n_hits = cnt;
     std::vector<uint2> hits(cnt);
-    if (cnt) CK(cudaMemcpy(hits.data(), h->d_hits.p + p.hit_off, cnt * sizeof(uint2), cudaMemcpyDeviceToHost));
+    const auto ovf = h->ovf_loc.find(h->tasks[0].plot[0]);      // a repetitive plot was re-run into the overflow buffer
+    const uint2* src = ovf != h->ovf_loc.end() ? h->d_ovf_hits.p + ovf->second : h->d_hits.p + p.hit_off;
+    if (cnt) CK(cudaMemcpy(hits.data(), src, cnt * sizeof(uint2), cudaMemcpyDeviceToHost));
     for (auto& v : hits) v.y &= HIT_Y_MASK;
     std::sort(hits.begin(), hits.end(), [](const uint2& a, const uint2& b2) { return a.x != b2.x ? a.x < b2.x : a.y < b2.y; });
     const int64_t nw = std::min<int64_t>(cap, cnt);
@@ -912,6 +1185,7 @@ int vapor_gpu_selfplot_qc(void* handle, const uint8_t* seq_bytes, const int64_t*
     std::vector<Plot> plots((size_t)n_seq);
     std::vector<int32_t> chunk_prefix((size_t)n_seq + 1, 0);
     std::vector<int64_t> strip_prefix((size_t)n_seq + 1, 0);
+    const int mode = h->k2_mode;
     const int k2_rows = k2_variant_rows(h->tile_variant);
     int64_t hash_off = 0, code_off = 0;
     for (int64_t i = 0; i < n_seq; ++i) {
@@ -919,48 +1193,74 @@ int vapor_gpu_selfplot_qc(void* handle, const uint8_t* seq_bytes, const int64_t*
         if (L < 0 || L >= (1ll << 27)) { h->err = "sequence length out of range (0 .. 2^27)"; return VAPOR_E_ARG; }
         if (k[i] < 1 || k[i] > K1_MAXK) { h->err = "window_size k must be 1..40"; return VAPOR_E_ARG; }
         Operand o{};
-        o.seq_begin = seq_off[i]; o.len = (int32_t)L; o.k = k[i]; o.flags = OPF_READ;
+        o.seq_begin = seq_off[i]; o.len = (int32_t)L; o.k = k[i]; o.flags = OPF_READ | OPF_TABLE;
         o.n = std::max(0, o.len - o.k + 1);
         o.hash_off = hash_off; o.code_off = code_off;
         hash_off += align4(o.n) + 8; code_off += (o.len + 8 + 15) & ~15;
         ops[i] = o;
         Plot p{};
         p.read_op = p.struct_op = (int32_t)i; p.miss = 0; p.n = p.m = o.n; p.cap = 0; p.kind = PLOT_QC; p.hit_off = i;
-        strip_prefix[i + 1] = strip_prefix[i] + cut_strips(p, k2_rows, nullptr);
+        if (mode == 0) strip_prefix[i + 1] = strip_prefix[i] + cut_strips(p, k2_rows, nullptr);
         plots[i] = p;
         chunk_prefix[i + 1] = chunk_prefix[i] + std::max(1, (o.len + K1_CHUNK - 1) / K1_CHUNK);
     }
-    h->plan_variant = h->tile_variant;
     const size_t ns = (size_t)n_seq;
+    std::vector<TabChunk> chunks; JoinPlan jp; int64_t table_bytes = 0;
+    if (mode == 1) {
+        std::vector<int32_t> op_chunk0;
+        table_bytes = build_chunks(ops, chunks, op_chunk0);
+        std::vector<Wave> one{Wave{0, 0, 0, (int64_t)ns, 0}};
+        build_join_items(plots, one, chunks, op_chunk0, jp);
+    }
     CK(h->d_seq.ensure((size_t)total + 64)); CK(h->d_ops.ensure(ns + 1)); CK(h->d_plots.ensure(ns + 1));
-    CK(h->d_chunk_prefix.ensure(ns + 1)); CK(h->d_strip_prefix.ensure(ns + 1));
+    CK(h->d_chunk_prefix.ensure(ns + 1));
     CK(h->d_hash.ensure((size_t)hash_off + 16)); CK(h->d_code.ensure((size_t)code_off + 64));
     CK(h->d_op_status.ensure(ns + 1)); CK(h->d_cnt.ensure(ns + 1)); CK(h->d_qc.ensure(ns * QC_WORDS));
-    CK(h->d_queue.ensure(4)); CK(h->d_misc.ensure(16));
+    CK(h->d_queue.ensure(4)); CK(h->d_ovf_flags.ensure(4)); CK(h->d_stats.ensure(4));
     if (total > 0) CK(cudaMemcpyAsync(h->d_seq.p, seq_bytes, (size_t)total, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_ops.p, ops.data(), ns * sizeof(Operand), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_plots.p, plots.data(), ns * sizeof(Plot), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_chunk_prefix.p, chunk_prefix.data(), (ns + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_strip_prefix.p, strip_prefix.data(), (ns + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (mode == 0) {
+        CK(h->d_strip_prefix.ensure(ns + 1));
+        CK(cudaMemcpyAsync(h->d_strip_prefix.p, strip_prefix.data(), (ns + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    } else if (!chunks.empty()) {
+        CK(h->d_chunks.ensure(chunks.size() + 1)); CK(h->d_items.ensure(jp.items.size() + 1));
+        CK(h->d_jplots.ensure(jp.jplots.size() + 1)); CK(h->d_table.ensure((size_t)table_bytes + 64));
+        CK(cudaMemcpyAsync(h->d_chunks.p, chunks.data(), chunks.size() * sizeof(TabChunk), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_items.p, jp.items.data(), jp.items.size() * sizeof(JoinItem), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_jplots.p, jp.jplots.data(), jp.jplots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    }
     std::vector<uint32_t> qc_init(ns * QC_WORDS, 0u);
     for (size_t i = 0; i < ns; ++i) { qc_init[i * QC_WORDS + 3] = 0xFFFFFFFFu; qc_init[i * QC_WORDS + 5] = 0xFFFFFFFFu; }
     CK(cudaMemcpyAsync(h->d_qc.p, qc_init.data(), qc_init.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->d_op_status.p, 0, (ns + 1) * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(h->d_cnt.p, 0, (ns + 1) * sizeof(uint32_t), h->stream));
     CK(cudaMemsetAsync(h->d_queue.p, 0, 4 * sizeof(unsigned long long), h->stream));
-    CK(cudaMemsetAsync(h->d_misc.p, 0, 16 * sizeof(uint32_t), h->stream));
+    CK(cudaMemsetAsync(h->d_ovf_flags.p, 0, 4 * sizeof(uint32_t), h->stream));
+    CK(cudaMemsetAsync(h->d_stats.p, 0, 4 * sizeof(unsigned long long), h->stream));
     k1_pack_kmers<<<chunk_prefix.back(), K1_THREADS, 0, h->stream>>>(
         h->d_seq.p, h->d_ops.p, h->d_chunk_prefix.p, (int)ns, h->d_hash.p, h->d_code.p, h->d_op_status.p);
     CK(cudaGetLastError());
-    if (strip_prefix.back() > 0) {
-        K2Params kp{};
-        kp.plots = h->d_plots.p; kp.ops = h->d_ops.p; kp.strip_prefix = h->d_strip_prefix.p;
-        kp.n_plots = (int)ns; kp.n_strips = strip_prefix.back(); kp.strip_base = 0;
-        kp.hash = h->d_hash.p; kp.code = h->d_code.p; kp.hits = nullptr; kp.cnt = h->d_cnt.p;
-        kp.queue = h->d_queue.p; kp.overflow = h->d_misc.p; kp.qc = h->d_qc.p;
-        launch_k2(h, kp);
-        CK(cudaGetLastError());
+    if (mode == 0) {
+        if (strip_prefix.back() > 0) {
+            K2Params kp{};
+            kp.plots = h->d_plots.p; kp.ops = h->d_ops.p; kp.strip_prefix = h->d_strip_prefix.p;
+            kp.n_plots = (int)ns; kp.n_strips = strip_prefix.back(); kp.strip_base = 0;
+            kp.hash = h->d_hash.p; kp.code = h->d_code.p; kp.hits = nullptr; kp.cnt = h->d_cnt.p;
+            kp.queue = h->d_queue.p; kp.overflow = h->d_ovf_flags.p; kp.qc = h->d_qc.p;
+            launch_k2(h, kp, h->tile_variant);
+        }
+    } else if (!chunks.empty()) {
+        k1b_build_tables<<<(unsigned)chunks.size(), K1B_THREADS, 0, h->stream>>>(h->d_chunks.p, h->d_ops.p, h->d_hash.p, h->d_table.p);
+        K2JParams kp{};
+        kp.items = h->d_items.p; kp.jplots = h->d_jplots.p; kp.chunks = h->d_chunks.p; kp.plots = h->d_plots.p;
+        kp.ops = h->d_ops.p; kp.hash = h->d_hash.p; kp.code = h->d_code.p; kp.table = h->d_table.p;
+        kp.hits = nullptr; kp.cnt = h->d_cnt.p; kp.overflow = h->d_ovf_flags.p; kp.qc = h->d_qc.p;
+        kp.evaluated = h->d_stats.p + 1;
+        launch_k2_join(h, jp, 0, kp);
     }
+    CK(cudaGetLastError());
     std::vector<int32_t> st(ns);
     CK(cudaMemcpyAsync(qc_init.data(), h->d_qc.p, qc_init.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(st.data(), h->d_op_status.p, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));

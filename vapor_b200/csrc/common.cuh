@@ -24,6 +24,7 @@ constexpr uint32_t H_MAX_VALID      = 0xFFFFFFFBu;
 // operand flags
 constexpr int OPF_UPPER = 1;   // str.upper() applied (ABS mode upper-cases ref/alt, Simple_function.pyx:183-184)
 constexpr int OPF_READ  = 2;   // read side: reverse complement also matches; invalid characters are an error
+constexpr int OPF_TABLE = 4;   // used as the structure side of a plot: the join kernel needs its sorted word table
 
 struct Operand {           // one (sequence, k, casing, role): owns a k-mer hash array and a code array
     int64_t seq_begin;     // byte offset in seq_bytes
@@ -57,6 +58,38 @@ struct Task {              // one read of one SV/allele
     int32_t len_ref, len_alt;   // full structure lengths: gate denominators (Simple_function.pyx:188-189)
     int32_t read_op;
     int32_t mode;
+};
+
+// ---- join variant of kernel 2 (k2_join.cuh) -----------------------------------------------------
+// A structure-side operand is cut into chunks of at most K2J_CH k-mer positions; kernel 1b turns every chunk into a
+// *table*: its valid words counting-sorted by the top `bits` bits of the 30-bit payload, the position of every
+// sorted word, and the 2^bits + 1 bucket offsets.  One blob per chunk, staged into shared memory by one TMA bulk copy:
+//   uint32 word[Lp] | uint16 pos[Lp] | uint16 off[2^bits + 8]       Lp = len rounded up to 8
+constexpr int K2J_CH       = 12288;            // positions per table chunk (pos fits 16 bits; blob <= 90 KB)
+constexpr int K2J_MIN_BITS = 8;
+constexpr int K2J_MAX_BITS = 12;
+
+struct TabChunk {
+    int64_t blob_off;      // byte offset of the blob in d_table (16-byte aligned)
+    int32_t op;            // operand the chunk belongs to
+    int32_t pos0;          // first k-mer position covered
+    int32_t len;           // positions covered (1 .. K2J_CH)
+    int32_t bits;          // bucket key bits
+    int32_t blob_bytes;    // multiple of 16
+    int32_t pad_;
+};
+__host__ __device__ inline int k2j_lp(int len) { return (len + 7) & ~7; }
+__host__ __device__ inline int k2j_bits(int len) {
+    int b = K2J_MIN_BITS;
+    while (b < K2J_MAX_BITS && (1 << b) < len) ++b;
+    return b;
+}
+__host__ __device__ inline int k2j_blob_bytes(int len, int bits) { return 6 * k2j_lp(len) + 2 * ((1 << bits) + 8); }
+
+struct JoinItem {          // one CTA of the join kernel: one table chunk against a few plots that use it
+    int32_t chunk;
+    int32_t jp_begin, jp_end;   // range in the launch's plot-id list
+    int32_t pad_;
 };
 
 // hits carry a flag bit in y while kernel 3 works on them (REDEF statistics)

@@ -23,7 +23,10 @@
 
 namespace vb {
 
-constexpr int K3_THREADS = 256;
+#ifndef K3_THREADS_N
+#define K3_THREADS_N 256
+#endif
+constexpr int K3_THREADS = K3_THREADS_N;
 
 // scratch layout in 32-bit words for a value range of NB: two group sets (y-x and y+x are clustered side by
 // side, so no flag has to travel through global memory between them) + one small histogram
@@ -494,6 +497,7 @@ __device__ __forceinline__ double k3_pair_score(const EvalResult& e) { return 1.
 struct K3Params {
     const Task* tasks;
     const int32_t* task_ids;     // tasks of this launch
+    const int32_t* out_ids;      // where task_ids[i]'s results go (null: at the task's own index)
     int n_ids;
     const Plot* plots;
     const uint32_t* cnt;         // hits per plot
@@ -574,14 +578,16 @@ k3_score_reads(const K3Params p)
     k3_setup_scratch(s, p.use_global ? p.gscratch + (size_t)blockIdx.x * k3_scratch_words(p.nb_cap) : s_dyn, p.nb_cap);
 
     for (int it = blockIdx.x; it < p.n_ids; it += gridDim.x) {
-        const int tix = p.task_ids[it];
-        const Task t = p.tasks[tix];
+        const int tin = p.task_ids[it];
+        const int tix = p.out_ids ? p.out_ids[it] : tin;
+        const Task t = p.tasks[tin];
         PlotView pv[4];
         #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (t.plot[i] >= 0) {
                 const Plot pl = p.plots[t.plot[i]];
-                pv[i].hits = p.hits + pl.hit_off; pv[i].H = p.cnt[t.plot[i]]; pv[i].n = pl.n; pv[i].m = pl.m;
+                // a plot that overflowed its first-pass capacity holds only `cap` dots: its task is scored again by redo_wave
+                pv[i].hits = p.hits + pl.hit_off; pv[i].H = min(p.cnt[t.plot[i]], pl.cap); pv[i].n = pl.n; pv[i].m = pl.m;
             } else { pv[i].hits = nullptr; pv[i].H = 0; pv[i].n = 0; pv[i].m = 0; }
         }
         const bool bad = p.op_status[t.read_op] != 0;
