@@ -23,7 +23,7 @@ def test_header_symbols_exported():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/vapor_b200.h but not exported"
     assert sorted(_native.EXPORTS) == declared
-    assert lib.vapor_b200_abi_version() == 1
+    assert lib.vapor_b200_abi_version() == 2
 
 
 def test_hit_mix_host_callable_matches_numpy():
