@@ -29,19 +29,20 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
-    """Compile the kernels + C-ABI with nvcc for sm_100a.  Returns the library path."""
-    if not force and not is_stale():
+def build_native(force: bool = False, verbose: bool = False, out: str = "", extra_flags=()) -> str:
+    """Compile the kernels + C-ABI with nvcc for sm_100a.  Returns the library path.  ``out`` / ``extra_flags``
+    build an experimental variant next to the product library (loaded with VAPOR_B200_LIB=...)."""
+    if not out and not force and not is_stale():
         return LIB
-    extra = os.environ.get("VAPOR_NVCC_EXTRA", "").split()          # experiments only, e.g. -DK2_MINB=6
+    extra = os.environ.get("VAPOR_NVCC_EXTRA", "").split() + list(extra_flags)     # experiments only, e.g. -DK2_MINB=6
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+          ["-o", out or LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libvapor_b200.so")
+# VAPOR_B200_LIB: another in-tree build of the same sources (kernel experiments: tools/build_variants.sh)
+LIB_PATH = os.environ.get("VAPOR_B200_LIB") or os.path.join(HERE, "csrc", "libvapor_b200.so")
 
 VAPOR_MODE_ABS, VAPOR_MODE_W10, VAPOR_MODE_REDEF, VAPOR_MODE_ABS_AND_W10 = 0, 1, 2, 3
 VAPOR_ST_SKIPPED, VAPOR_ST_SCORED, VAPOR_ST_BADREAD = 0, 1, 2

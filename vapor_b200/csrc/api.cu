@@ -63,7 +63,7 @@ const int k3_class_cap[K3_NCLASS - 1] = {4096, 16384, 26624, 110000};
 
 // join-kernel launch classes by table blob size (dynamic shared memory of the launch)
 constexpr int K2J_NCLASS = 3;
-const int k2j_class_cap[K2J_NCLASS] = {16640, 45056, 81936};
+const int k2j_class_cap[K2J_NCLASS] = {16640, k2j_blob_bytes(6144, k2j_bits(6144)), k2j_blob_bytes(K2J_CH, k2j_bits(K2J_CH))};
 
 // the k2 plan of a set of plots: strips for the tile kernel, or table chunks + items for the join kernel
 struct JoinPlan {
@@ -261,8 +261,16 @@ void build_join_items(const std::vector<Plot>& plots, const std::vector<Wave>& w
                 jp.jplots.insert(jp.jplots.end(), sorted.begin() + g0, sorted.begin() + g1);
                 for (int32_t c = op_chunk0[op]; c < (int32_t)chunks.size() && chunks[c].op == op; ++c) {
                     const int k = k2j_class_of(chunks[c].blob_bytes);
-                    for (int32_t a = 0; a < g1 - g0; a += K2J_PLOTS_PER_ITEM)
-                        cls[k].push_back(JoinItem{c, jbase + a, jbase + std::min<int32_t>(a + K2J_PLOTS_PER_ITEM, g1 - g0), 0});
+                    // runs of plots of about K2J_WORDS_PER_ITEM read words (at most K2J_PLOTS_PER_ITEM plots): items of similar length
+                    int32_t a = 0;
+                    while (a < g1 - g0) {
+                        int32_t e = a; int64_t words = 0;
+                        while (e < g1 - g0 && e - a < K2J_PLOTS_PER_ITEM && (e == a || words + plots[sorted[g0 + e]].n <= K2J_WORDS_PER_ITEM)) {
+                            words += plots[sorted[g0 + e]].n; ++e;
+                        }
+                        cls[k].push_back(JoinItem{c, jbase + a, jbase + e, 0});
+                        a = e;
+                    }
                 }
             }
         }

@@ -67,7 +67,10 @@ struct Task {              // one read of one SV/allele
 //   uint32 word[Lp] | uint16 pos[Lp] | uint16 off[2^bits + 8]       Lp = len rounded up to 8
 constexpr int K2J_CH       = 12288;            // positions per table chunk (pos fits 16 bits; blob <= 90 KB)
 constexpr int K2J_MIN_BITS = 8;
-constexpr int K2J_MAX_BITS = 12;
+#ifndef K2J_MAX_BITS_N
+#define K2J_MAX_BITS_N 12
+#endif
+constexpr int K2J_MAX_BITS = K2J_MAX_BITS_N;
 
 struct TabChunk {
     int64_t blob_off;      // byte offset of the blob in d_table (16-byte aligned)

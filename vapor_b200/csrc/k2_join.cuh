@@ -11,10 +11,11 @@
 //   k2_join_match: one CTA stages one table in shared memory with ONE TMA bulk copy (cp.async.bulk + mbarrier)
 //       and streams the read words of every plot that uses the table past it, 128 read words per warp and step,
 //       straight from HBM/L2 in natural order (coalesced, four loads in flight per lane).  A lane looks its
-//       word's bucket up (two 16-bit offsets) and compares the word with the bucket's entries; the warp walks
-//       the buckets in lock-step (ballot), parks matched cells in the per-warp queue of k2_tile.cuh and emits
-//       them with k2_flush (confirmation of hashed words, multiplicity of palindromes, QC counters, one atomic
-//       per batch) -- the hit set is identical to the tile kernel's and to the reference's, only its order differs.
+//       word's bucket up (two 16-bit offsets) and compares the word with the bucket's entries (1.3 on average), each
+//       lane on its own; a matched cell takes a slot of the per-warp queue with a shared-memory atomic, and the warp
+//       emits the queue with k2_flush of k2_tile.cuh (confirmation of hashed words, multiplicity of palindromes, QC
+//       counters, one global atomic per batch) -- the hit set is identical to the tile kernel's and to the
+//       reference's, only its order differs.
 //
 // Cells evaluated = sum over read words of the size of their bucket (about n * (1 + m / 2^bits) per plot instead of
 // n * m); the kernel counts them (K2JParams::evaluated) so that throughput can be quoted on evaluated cells.
@@ -28,7 +29,8 @@ constexpr int K1B_THREADS = 256;
 constexpr int K2J_WARPS   = 8;
 constexpr int K2J_THREADS = 32 * K2J_WARPS;
 constexpr int K2J_UNROLL  = 4;                  // read words per lane and step (loads in flight)
-constexpr int K2J_PLOTS_PER_ITEM = 8;           // plots one CTA streams past its table
+constexpr int K2J_PLOTS_PER_ITEM = 8;           // most plots one CTA streams past its table ...
+constexpr int K2J_WORDS_PER_ITEM = 24576;       // ... and about how many read words: items of similar length
 
 __host__ __device__ __forceinline__ uint32_t k2j_key(uint32_t word, int bits) {
     return (word & 0x3FFFFFFFu) >> (30 - bits);
@@ -108,15 +110,20 @@ struct K2JParams {
 };
 
 #ifndef K2J_MINB
-#define K2J_MINB 3
+#define K2J_MINB 4
 #endif
+constexpr int K2J_QCAP = 96;                    // per-warp queue of matched cells awaiting emission
+
+__device__ __forceinline__ uint32_t k2j_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t k2j_lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return (uint32_t)v; }
 
 __global__ void __launch_bounds__(K2J_THREADS, K2J_MINB)
 k2_join_match(const K2JParams p)
 {
     extern __shared__ __align__(128) uint8_t s_blob[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ __align__(8) uint2 s_queue[K2J_WARPS][K2_QCAP];
+    __shared__ __align__(8) uint2 s_queue[K2J_WARPS][K2J_QCAP];
+    __shared__ uint32_t s_qn[K2J_WARPS];
     __shared__ K2Strip s_strip[K2J_WARPS];
     __shared__ unsigned long long s_eval;
 
@@ -130,15 +137,17 @@ k2_join_match(const K2JParams p)
         mbar_expect_tx(&s_bar, (uint32_t)ch.blob_bytes);
         tma_bulk_g2s(s_blob, p.table + ch.blob_off, (uint32_t)ch.blob_bytes, &s_bar);
     }
+    if (lane == 0) s_qn[warp] = 0u;
     __syncthreads();                                     // the barrier is initialised before anyone waits on it
     const int lp = k2j_lp(ch.len);
-    const uint32_t* tw = reinterpret_cast<const uint32_t*>(s_blob);
-    const uint16_t* tp = reinterpret_cast<const uint16_t*>(s_blob + 4 * (size_t)lp);
-    const uint16_t* toff = reinterpret_cast<const uint16_t*>(s_blob + 6 * (size_t)lp);
-    const int bits = ch.bits;
+    const uint32_t a_tw = smem_u32(s_blob);              // sorted words
+    const uint32_t a_tp = a_tw + 4u * (uint32_t)lp;      // their positions
+    const uint32_t a_off = a_tw + 6u * (uint32_t)lp;     // bucket offsets
+    const int shift = 30 - ch.bits;
     uint2* queue = s_queue[warp];
+    uint32_t* qn = &s_qn[warp];
     K2Strip& st = s_strip[warp];
-    unsigned long long evaluated = 0;
+    uint32_t evaluated = 0;
     bool waited = false;
 
     int blk0 = 0;                                        // 128-word read blocks of the item's earlier plots
@@ -151,9 +160,9 @@ k2_join_match(const K2JParams p)
         blk0 += nblk;
         if (b >= nblk || pl.m <= 0) continue;            // warp-uniform
         const Operand opr = p.ops[pl.read_op];
-        const Operand ops_ = p.ops[pl.struct_op];
         __syncwarp();
         if (lane == 0) {
+            const Operand ops_ = p.ops[pl.struct_op];
             st.code_read = p.code + opr.code_off; st.code_struct = p.code + ops_.code_off + pl.miss;
             st.cnt = p.cnt + pid; st.hits = p.hits + pl.hit_off; st.overflow = p.overflow; st.cap = pl.cap; st.k = opr.k; st.swap = false;
             st.qc = (pl.kind & PLOT_QC) ? p.qc + pl.hit_off * QC_WORDS : nullptr;
@@ -161,7 +170,6 @@ k2_join_match(const K2JParams p)
         __syncwarp();
         const uint32_t* rw = p.hash + opr.hash_off;
         const int xoff = ch.pos0 - pl.miss;              // structure coordinate of table position 0 after the cut
-        int qn = 0;
         for (; b < nblk; b += K2J_WARPS) {
             const int base = b * 32 * K2J_UNROLL + lane;
             uint32_t r[K2J_UNROLL];
@@ -171,34 +179,45 @@ k2_join_match(const K2JParams p)
             #pragma unroll
             for (int u = 0; u < K2J_UNROLL; ++u) {
                 const uint32_t word = r[u];
-                int idx = 0, end = 0;
+                uint32_t idx = 0, end = 0;
                 if (word <= H_MAX_VALID) {
-                    const uint32_t key = k2j_key(word, bits);
-                    idx = toff[key]; end = toff[key + 1];
+                    const uint32_t ka = a_off + 2u * ((word & 0x3FFFFFFFu) >> shift);
+                    idx = k2j_lds16(ka); end = k2j_lds16(ka + 2u);
                 }
-                evaluated += (unsigned)(end - idx);
-                while (__ballot_sync(0xFFFFFFFFu, idx < end)) {
-                    bool hit = false;
-                    int x = 0;
-                    if (idx < end && tw[idx] == word) { x = xoff + (int)tp[idx]; hit = x >= 0; }
-                    const unsigned hm = __ballot_sync(0xFFFFFFFFu, hit);
-                    if (hm) {
-                        if (qn + __popc(hm) > K2_QCAP) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
-                        if (hit) queue[qn + __popc(hm & ((1u << lane) - 1u))] =
-                            make_uint2((uint32_t)x | (word & 0xC0000000u), (uint32_t)(base + 32 * u));
-                        qn += __popc(hm);
+                evaluated += end - idx;
+                // every lane scans its own bucket; a matched cell takes a queue slot with a shared-memory atomic.  A lane that
+                // finds the queue full stops at that entry: the warp then empties the queue and the lane carries on.
+                while (true) {
+                    for (; idx < end; ++idx) {
+                        if (k2j_lds32(a_tw + 4u * idx) != word) continue;
+                        const int x = xoff + (int)k2j_lds16(a_tp + 2u * idx);
+                        if (x < 0) continue;
+                        const uint32_t slot = atomicAdd(qn, 1u);
+                        if (slot >= (uint32_t)K2J_QCAP) break;
+                        queue[slot] = make_uint2((uint32_t)x | (word & 0xC0000000u), (uint32_t)(base + 32 * u));
                     }
-                    ++idx;
+                    __syncwarp();                                    // every lane's slots and queue entries are visible
+                    const unsigned more = __ballot_sync(0xFFFFFFFFu, idx < end);
+                    const uint32_t have = min(*qn, (uint32_t)K2J_QCAP);
+                    if (more == 0u && have <= (uint32_t)(K2J_QCAP - 48)) break;
+                    __syncwarp();
+                    k2_flush(st, queue, (int)have, lane);
+                    __syncwarp();
+                    if (lane == 0) *qn = 0u;
+                    __syncwarp();
+                    if (more == 0u) break;
                 }
             }
         }
         __syncwarp();
-        if (qn) k2_flush(st, queue, qn, lane);
+        const uint32_t have = min(*qn, (uint32_t)K2J_QCAP);
+        if (have) { k2_flush(st, queue, (int)have, lane); __syncwarp(); if (lane == 0) *qn = 0u; }
     }
     if (!waited) mbar_wait(&s_bar, 0);                   // nobody leaves while the bulk copy may still be landing
+    unsigned long long ev = evaluated;
     #pragma unroll
-    for (int o = 16; o; o >>= 1) evaluated += __shfl_xor_sync(0xFFFFFFFFu, evaluated, o);
-    if (lane == 0 && evaluated) atomicAdd(&s_eval, evaluated);
+    for (int o = 16; o; o >>= 1) ev += __shfl_xor_sync(0xFFFFFFFFu, ev, o);
+    if (lane == 0 && ev) atomicAdd(&s_eval, ev);
     __syncthreads();
     if (threadIdx.x == 0 && s_eval && p.evaluated) atomicAdd(p.evaluated, s_eval);
 }
