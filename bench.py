@@ -1,27 +1,40 @@
 #!/usr/bin/env python
 """bench.py -- reads scored/s of the VaPoR per-read scoring path on N B200s (one JSON line).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n-sv M]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2|3|4|5] [--n-sv M] [--weak]
 
-Workload (BASELINE.json configs[1]): 10k simple SVs (DEL/TANDUP/INV/INS cycled, 50 bp-5 kb), 20 reads per
-SV (30x CLR-like coverage after the reference's 20-read cap), ~15 % read error, k = 10, generated by
-vapor_b200.synth (seeded; SV i derives from default_rng([seed, i])).  A *step* is one pass of the hot path
-(kernels 1-4) over that whole batch.  Under torchrun every rank scores its own 10k-SV shard of the SV list
-(SVs rank*M .. rank*M+M-1; independent work queues, no data-path collective) -> "scaling": "weak".
+Workloads (BASELINE.json `configs`, seeded: SV i derives from default_rng([20261018 + config index, i])):
+  --config 5 (default)  configs[4]: one genome-scale 100 000-SV list (DEL/TANDUP/INV/INS cycled, 50 bp-5 kb, 20
+                        CLR-like reads per SV at 15 % error = 30x coverage after the reference's 20-read cap, k = 10),
+                        SV-sharded over the N GPUs -- the configuration the north_star's target is quoted on.
+  --config 2            configs[1]: 10 000 simple SVs of the same kind.
+  --config 3            configs[2]: 10 000 complex events (DEL_INV, DUP_INV, DISDUP, DEL_DUP_INV, multi-allele
+                        `Other=` records with 2-3 alternative haplotypes, junction fallbacks; modes ABS/REDEF/W10 mixed).
+  --config 4            configs[3]: 400 large events, 10-100 kb windows, k cycled over 10/20/30/40.
+A *step* is one pass of the hot path (kernels 1-4) over the whole SV list.
 
-  value  : reads scored/s with the batch resident in HBM (vapor_gpu_upload once, vapor_gpu_run per step),
+Multi-GPU (torchrun, one process per GPU): "scaling": "strong".  Every rank computes the cost of every SV of the list
+(vapor_b200.synth.workload_costs, no sequence needed), takes its part from the product's partitioner
+(vapor_b200.multi.partition_svs: greedy longest-processing-time on recurrence cells), builds and scores only that
+part, and writes its results to their input positions in result arrays shared by all ranks
+(vapor_b200.multi.SharedResults, /dev/shm): after the barrier rank 0 holds the whole list's results in input order.
+No data-path collective; NCCL carries the barrier and the max-over-ranks of the timings only.  `output_checksum`
+(SHA-256 over the gathered hit checksums, scores, statuses and genotype calls) must be identical at N = 1/2/4/8.
+--weak gives every rank its own M SVs instead (SVs rank*M ...), as round 1 measured.
+
+  value  : reads scored/s with every rank's part resident in HBM (vapor_gpu_upload once, vapor_gpu_run per step),
            timed with CUDA events on the library's stream, max over ranks.
-  e2e    : the same metric through the public call Engine.score() = vapor_gpu_score with HOST (pinned)
-           buffers: host planning + H2D + kernels + D2H inside the timed region, every step.
-  roofline: the tile kernel against the measured INT32 ALU issue rate of this GPU (the north_star's bound
-           for this kernel: integer compare work, not HBM, not tensor cores) + kernel 1 against HBM.
+  e2e    : the same metric through the public call (vapor_gpu_score on pinned HOST buffers: host planning + H2D +
+           kernels + D2H every step) plus the gather into input order, wall clock between barriers, max over ranks.
+  roofline: the dominant kernel of the step (by CUDA-event time) against its bound; `kernels` lists all of them.
   cpu_baseline / --impl reference: the reference's own code (oracle/_ref = Cython build of the untouched
-           Simple_function.pyx when it travelled with the snapshot, else the numpy oracle port) on all host
-           cores, on a bounded prefix of the same SV list.
+           Simple_function.pyx when it travelled with the snapshot, else the numpy oracle port) on all host cores, on a
+           stratified sample of the same SV list.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -35,16 +48,48 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-SEED = 20261018 + 1            # seed = 20261018 + config index
-N_SV_DEFAULT = 10000
+SEED0 = 20261018               # seed = 20261018 + config index
 READS_PER_SV = 20
-SIZE_RANGE = (50, 5000)
 METRIC = "reads_scored_per_sec"
 UNIT = "reads/s"
+
+CONFIGS = {
+    2: dict(index=1, recipe="simple", n_sv=10000, size_range=(50, 5000), k=(10,),
+            name="BASELINE configs[1]: 10k simple SVs DEL/TANDUP/INV/INS 50bp-5kb, 20 CLR-like reads (15% error) per SV, k=10"),
+    3: dict(index=2, recipe="complex", n_sv=10000, size_range=(200, 5000), k=(10,),
+            name="BASELINE configs[2]: 10k complex events (DEL_INV, DUP_INV, DISDUP, DEL_DUP_INV, 2-3-allele Other= records, "
+                 "junction fallbacks), 20 CLR-like reads per event scored against every alternative haplotype, modes ABS/REDEF/W10, k=10"),
+    4: dict(index=3, recipe="large", n_sv=400, size_range=(10000, 100000), k=(10, 20, 30, 40),
+            name="BASELINE configs[3]: 400 large events (DEL/TANDUP/INV/INS) with 10-100 kb windows, 20 CLR-like reads each, "
+                 "k cycled over 10/20/30/40"),
+    5: dict(index=4, recipe="simple", n_sv=100000, size_range=(50, 5000), k=(10,),
+            name="BASELINE configs[4]: genome-scale 100k-SV list (DEL/TANDUP/INV/INS 50bp-5kb), 20 CLR-like reads (15% error) "
+                 "per SV = 30x after the 20-read cap, k=10, SV-sharded across the GPUs"),
+}
 
 
 def _dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def _cfg(args):
+    c = dict(CONFIGS[args.config])
+    if args.n_sv > 0:
+        c["n_sv"] = args.n_sv
+    c["seed"] = SEED0 + c["index"]
+    return c
+
+
+def _gen_kwargs(c):
+    return dict(seed=c["seed"], recipe=c["recipe"], size_range=c["size_range"], reads_per_sv=READS_PER_SV, k_choices=c["k"])
+
+
+def _config_json(args, c, world):
+    """Names the workload; identical for both arms (the reference arm times a bounded sample of it)."""
+    return {"workload": c["name"], "config": args.config, "n_sv": int(c["n_sv"]) * (world if args.weak else 1),
+            "scaling_mode": "weak: n_sv per GPU" if args.weak else "strong: one SV list, LPT-partitioned by vapor_b200.multi.partition_svs",
+            "reads_per_sv": READS_PER_SV, "seed": c["seed"],
+            "l2": "inputs larger than L2 (sequence + k-mer word arrays >> 126 MB at the default sizes); no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -92,7 +137,7 @@ def cpu_score_sample(batch, cores: int, pool=None):
     # longest first: the per-read cost spans two orders of magnitude
     order = sorted(range(len(tasks)), key=lambda i: -len(tasks[i][0]) * (len(tasks[i][1]) + len(tasks[i][2])))
     t0 = time.perf_counter()
-    if cores <= 1:
+    if cores <= 1 or pool is None:
         out = [_cpu_task(tasks[i]) for i in order]
     else:
         out = pool.map(_cpu_task, [tasks[i] for i in order], chunksize=1)
@@ -116,47 +161,81 @@ def _make_pool(cores):
     return mp.get_context("fork").Pool(cores) if cores > 1 else None
 
 
+def stratified_ids(costs: np.ndarray, n_pick: int, offset: int = 0) -> np.ndarray:
+    """`n_pick` SVs spread evenly over the list ordered by cost (every cost decile and, because types cycle with
+    the index, every SV type is represented); `offset` rotates the choice so successive samples are disjoint."""
+    order = np.argsort(costs, kind="stable")
+    n = len(order)
+    n_pick = min(n_pick, n)
+    pos = (np.arange(n_pick) * n // n_pick + offset) % n
+    return np.sort(order[pos])
+
+
+def _composition(w):
+    types = sorted(set(w.sv_type))
+    bins = [0, 500, 2000, 5000, 20000, 50000, 10 ** 9]
+    out = {}
+    for t in types:
+        lens = w.sv_len[[i for i, x in enumerate(w.sv_type) if x == t]]
+        hist = np.histogram(lens, bins=bins)[0]
+        out[t] = {f"<{b}": int(h) for b, h in zip(bins[1:], hist) if h}
+    return out
+
+
 def run_reference_arm(args):
-    """--impl reference: time the reference's CPU implementation on all host cores (rank 0 only)."""
+    """--impl reference: time the reference's CPU implementation on all host cores (rank 0 only).
+    Every step scores a fresh stratified sample of the configured SV list, sized for a few seconds of all-core work."""
     rank, _, world = _dist_env()
     if rank != 0:
         return
     from vapor_b200 import synth
+    c = _cfg(args)
     cores = os.cpu_count() or 1
     impl, kind = _cpu_impl()
-    n_sample = args.ref_svs if args.ref_svs > 0 else max(4, min(2 * cores, 256))
-    w = synth.make_workload(n_sample, seed=SEED, size_range=SIZE_RANGE, reads_per_sv=READS_PER_SV,
-                            workers=min(cores, 32))
+    gk = _gen_kwargs(c)
+    n_list = c["n_sv"] * (world if args.weak else 1)
+    costs = synth.workload_costs(min(n_list, 20000), **{k: v for k, v in gk.items()})
+    # cells one step should hold: about ref_seconds of all-core work at the reference's measured ~2.5e8 cells/s/core
+    budget_cells = args.ref_seconds * cores * 2.5e8
+    mean_cost = float(costs.mean())
+    n_sample = args.ref_svs if args.ref_svs > 0 else int(max(4, min(len(costs) // max(1, args.warmup + args.steps), budget_cells / mean_cost)))
     pool = _make_pool(cores)
-    times = []
+    times, reads, cells, n_svs = [], 0, 0, 0
+    comp = {}
+    single = None
     for it in range(args.warmup + args.steps):
+        ids = stratified_ids(costs, n_sample, offset=it)
+        w = synth.make_workload(0, sv_ids=ids, workers=min(cores, 16), **gk)
+        if single is None:                                   # single-core rate on a small sub-sample (not part of the timed steps)
+            sub = w.batch.shard(range(min(3, w.batch.n_sv)))
+            dt1, _ = cpu_score_sample(sub, 1, None)
+            single = {"reads_per_s": sub.n_task / dt1, "reads": int(sub.n_task)}
         dt, _ = cpu_score_sample(w.batch, cores, pool)
         if it >= args.warmup:
-            times.append(dt)
+            times.append(dt); reads += w.batch.n_task; cells += w.cells; n_svs += w.batch.n_sv
+            for t, d in _composition(w).items():
+                for b, h in d.items():
+                    comp.setdefault(t, {}).setdefault(b, 0)
+                    comp[t][b] += h
     if pool is not None:
         pool.close()
     total = sum(times)
-    value = w.batch.n_task * len(times) / total
-    sample = (f"first {n_sample} SVs ({w.batch.n_task} reads, {w.cells:.3e} cells) of the same seeded SV list per step, "
+    value = reads / total
+    sample = (f"{n_svs} SVs ({reads} reads, {cells:.3e} cells) in {len(times)} disjoint stratified samples of {n_sample} SVs of the "
+              f"same seeded SV list (evenly spaced over the list ordered by cost), {total:.1f} s of wall time, "
               f"{getattr(impl, '__vapor_kind__', 'numpy-oracle')}, per-read tasks over a {cores}-process pool")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": _config(args.n_sv),
-        "sample": {"n_sv": n_sample, "reads": int(w.batch.n_task), "cells": int(w.cells)},
-        "cells_per_sec": w.cells * len(times) / total,
+        "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": _config_json(args, c, world),
+        "sample": {"n_sv": n_svs, "reads": int(reads), "cells": int(cells), "wall_s": total, "composition_type_x_svlen": comp},
+        "cells_per_sec": cells / total,
+        "single_core": single,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     _emit(line)
-
-
-def _config(n_sv):
-    """Names the workload; identical for both arms (the reference arm times a bounded prefix of it)."""
-    return {"workload": "BASELINE configs[1]: 10k simple SVs DEL/TANDUP/INV/INS 50bp-5kb, 20 CLR-like reads (15% error) per SV, k=10",
-            "n_sv_per_gpu": int(n_sv), "reads_per_gpu": int(n_sv) * READS_PER_SV, "seed": SEED,
-            "l2": "inputs larger than L2 (sequence + k-mer word arrays >> 126 MB at the default size); no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -210,20 +289,47 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def output_checksum(res) -> str:
+    """SHA-256 over the gathered results that must not depend on how the list was sharded."""
+    h = hashlib.sha256()
+    for f in ("task_hitsum", "task_hits", "task_status", "task_score", "task_stat", "sv_gt", "sv_nscore", "sv_qs", "sv_gs", "sv_gq"):
+        h.update(np.ascontiguousarray(getattr(res, f)).tobytes())
+    return h.hexdigest()
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
     rank, local_rank, world = _dist_env()
     # the synthetic workload is made first: it forks worker processes, which is safest before CUDA / NCCL exist
-    from vapor_b200 import synth
-    from vapor_b200.engine import Engine
-    n_sv = args.n_sv
+    from vapor_b200 import multi, synth
+    from vapor_b200.engine import Engine, Pipeline
+    c = _cfg(args)
+    gk = _gen_kwargs(c)
     cores = os.cpu_count() or 1
     t_gen = time.perf_counter()
-    w = synth.make_workload(n_sv, seed=SEED, size_range=SIZE_RANGE, reads_per_sv=READS_PER_SV,
-                            workers=max(1, min(32, cores // max(world, 1))), first_sv=rank * n_sv)
+    if args.weak:
+        n_list = c["n_sv"] * world
+        my_ids = np.arange(rank * c["n_sv"], (rank + 1) * c["n_sv"], dtype=np.int64)
+        costs, ntask = synth.workload_costs(n_list, with_tasks=True, **gk) if world > 1 else (None, None)
+        parts = [np.arange(r * c["n_sv"], (r + 1) * c["n_sv"], dtype=np.int64) for r in range(world)]
+    else:
+        n_list = c["n_sv"]
+        costs, ntask = synth.workload_costs(n_list, with_tasks=True, **gk)
+        parts = multi.partition_svs(costs, world)            # every rank computes the same partition
+        my_ids = parts[rank]
+    w = synth.make_workload(0, sv_ids=my_ids, workers=max(1, min(32, cores // max(world, 1))), **gk)
     t_gen = time.perf_counter() - t_gen
+    if costs is not None:
+        part_cells = np.array([float(costs[p].sum()) for p in parts])
+        sv_task_off = np.zeros(n_list + 1, dtype=np.int64)
+        np.cumsum(ntask, out=sv_task_off[1:])
+    else:
+        part_cells = np.array([float(w.cells)])
+        sv_task_off = w.batch.sv_task_off
+    n_task_list = int(sv_task_off[-1])
+
     import torch
     dist = None
     if world > 1:
@@ -238,32 +344,50 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(local_rank)
 
-    def max_over_ranks(x: float) -> float:
+    def reduce(x: float, op) -> float:
         if dist is None:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def max_over_ranks(x):
+        return reduce(x, dist.ReduceOp.MAX) if dist is not None else x
+
+    def sum_over_ranks(x):
+        return reduce(x, dist.ReduceOp.SUM) if dist is not None else x
 
     eng = Engine(local_rank)
+    opts = {}
     if args.tile_variant >= 0:
-        eng.set_option("tile_variant", args.tile_variant)
+        opts["tile_variant"] = args.tile_variant
     if args.k2_mode >= 0:
-        eng.set_option("k2_mode", args.k2_mode)
-    if args.k2_ctas_per_sm > 0:
-        eng.set_option("k2_ctas_per_sm", args.k2_ctas_per_sm)
+        opts["k2_mode"] = args.k2_mode
     if args.hit_budget_gb > 0:
-        eng.set_option("hit_budget_bytes", int(args.hit_budget_gb * (1 << 30)))
+        opts["hit_budget_bytes"] = int(args.hit_budget_gb * (1 << 30))
+    if args.k2_ctas_per_sm > 0:
+        opts["k2_ctas_per_sm"] = args.k2_ctas_per_sm
+    for k_, v_ in opts.items():
+        eng.set_option(k_, v_)
     batch = eng.pin_batch(w.batch)                      # inputs live in pinned host memory
     res = eng.pinned_results(batch.n_task, batch.n_sv)
     n_reads = batch.n_task
+
+    # the gathered results of the whole list, in input order, shared by all ranks (rank 0 owns them)
+    tag = f"{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}"
+    shared = None
+    if world > 1:
+        if rank == 0:
+            shared = multi.SharedResults(tag, n_task_list, n_list, create=True)
+        barrier()
+        if rank != 0:
+            shared = multi.SharedResults(tag, n_task_list, n_list, create=False)
+        my_tix = multi.part_task_index(sv_task_off, my_ids)
+
+    def gather(r):
+        """This rank's results to their input positions in the shared arrays (at N = 1 they are in input order already)."""
+        if shared is not None:
+            multi.scatter_part(shared.results, my_tix, my_ids, r)
 
     # ---- resident timing: upload once, K x run() ---------------------------------------------------
     eng.upload(batch)
@@ -272,149 +396,178 @@ def run_gpu_arm(args):
     barrier()
     sampler = ClockSampler(local_rank)
     t0 = time.perf_counter()
-    dev_ms, tile_ms, pack_ms, score_ms, geno_ms, launches = 0.0, 0.0, 0.0, 0.0, 0.0, 0
+    acc = {"total_ms": 0.0, "tile_ms": 0.0, "pack_ms": 0.0, "table_ms": 0.0, "score_ms": 0.0, "genotype_ms": 0.0, "launches": 0}
     for _ in range(args.steps):
         eng.run()
         tm = eng.timings()
-        dev_ms += tm["total_ms"]; tile_ms += tm["tile_ms"]; pack_ms += tm["pack_ms"]
-        score_ms += tm["score_ms"]; geno_ms += tm["genotype_ms"]; launches += tm["launches"]
+        for k_ in acc:
+            acc[k_] += tm[k_]
     barrier()
     t1 = time.perf_counter()
     wall_resident = t1 - t0
     clocks = sampler.stop(t0, t1)
     eng.fetch(res)
     tm_last = eng.timings()
-    dev_s = max_over_ranks(dev_ms * 1e-3)
+    dev_s = max_over_ranks(acc["total_ms"] * 1e-3)
     total_reads = sum_over_ranks(float(n_reads))
     total_cells = sum_over_ranks(float(tm_last["cells"]))
+    total_eval = sum_over_ranks(float(tm_last["evaluated_cells"]))
     value = total_reads * args.steps / dev_s
 
-    # ---- end to end: host buffers -> public API -> host results, every step --------------------------------
-    # (a) one blocking call per step (Engine.score = vapor_gpu_score): plan + H2D + kernels + D2H back to back
+    # ---- end to end: host buffers -> public API -> host results in input order, every step -----------------------
+    # (a) one blocking call per step (Engine.score_into = vapor_gpu_score): plan + H2D + kernels + D2H, then the gather
     for _ in range(max(1, args.warmup // 2)):
-        eng.score_into(batch, res)
+        gather(eng.score_into(batch, res))
     barrier()
     te0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.score_into(batch, res)
+        gather(eng.score_into(batch, res))
     barrier()
     e2e_single_s = max_over_ranks(time.perf_counter() - te0)
     tm_e2e = eng.timings()
     # (b) the same steps through engine.Pipeline (two handles, double-buffered): every step still plans, copies its
-    #     inputs in from pinned host memory and copies its results out, but that overlaps the previous step's kernels
-    from vapor_b200.engine import Pipeline
-    opts = {}
-    if args.tile_variant >= 0:
-        opts["tile_variant"] = args.tile_variant
-    if args.k2_mode >= 0:
-        opts["k2_mode"] = args.k2_mode
-    if args.hit_budget_gb > 0:
-        opts["hit_budget_bytes"] = int(args.hit_budget_gb * (1 << 30))
+    #     inputs in from pinned host memory, copies its results out and gathers them, overlapped with the previous step's kernels
     pipe = Pipeline(local_rank, depth=2, options=opts)
     res2 = [res, eng.pinned_results(batch.n_task, batch.n_sv)]
-    pipe.map([batch] * 2, res2)                                         # warm-up: buffers of both handles allocated
+    pipe.map([batch] * 2, res2, after=gather)                           # warm-up: buffers of both handles allocated
     barrier()
     te0 = time.perf_counter()
-    outs = pipe.map([batch] * args.steps, [res2[i % 2] for i in range(args.steps)])
+    pipe.map([batch] * args.steps, [res2[i % 2] for i in range(args.steps)], after=gather)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - te0)
     pipe.close()
     e2e_value = total_reads * args.steps / e2e_s
-    launches_total = sum_over_ranks(float(launches))
+    launches_total = sum_over_ranks(float(acc["launches"]))
+    gathered = shared.results if shared is not None else res
+    checksum = output_checksum(gathered) if rank == 0 else None
 
-    # ---- roofline of the dominant kernel (tile kernel) against the measured INT32 issue rate --------
-    alu_peak = max(eng.int_peak(1), eng.int_peak(2))          # LOP3 / IADD3 lane-ops/s: the alu pipe alone
-    dual_peak = max(eng.int_peak(3), eng.int_peak(4))         # alu + fma pipes together: LOP3 + IMAD streams / the tile loop in isolation
-    int_peak = max(alu_peak, dual_peak)
-    k_arr = batch.task_k.astype(np.int64)
-    ops_per_cell = float(np.mean((2 * k_arr + 31) // 32))     # ceil(2k/32) 32-bit equality tests per cell
-    tile_s = tile_ms * 1e-3 / args.steps
-    achieved = tm_last["cells"] * ops_per_cell / tile_s
-    traffic = None                                            # DRAM bytes per tile-kernel launch, from the committed ncu capture
-    prof = os.path.join(ROOT, "profiles", "k2_traffic.json")
-    if os.path.exists(prof):
-        try:                                                  # measured bytes/cell (ncu --set full, 400-SV launch) x cells of one launch here
-            traffic = json.load(open(prof)).get("dram_bytes_per_cell") * tm_last["cells"] / max(1, tm_last["n_waves"])
-        except Exception:
-            traffic = None
+    # ---- roofline ---------------------------------------------------------------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    pack_bytes = tm_last["bases"] * 2.0 + 4.0 * tm_last["bases"]      # 1 B/base read + 1 B/base code + 4 B/position word written
-    pack_s = pack_ms * 1e-3 / args.steps
-    sm_count = 148
-    nominal = sm_count * 128 * 1.965e9                         # 4 SMSPs x 1 warp instruction/clk x 32 lanes at 1965 MHz
-    roofline = {"kernel": "k2_tile_match", "bound": "int32_issue", "achieved": achieved / 1e9, "peak": int_peak / 1e9,
-                "unit": "Gop/s", "frac": achieved / int_peak, "traffic": traffic,
-                "note": "achieved = cells x ceil(2k/32) 32-bit equality tests per launch / CUDA-event time of the tile kernel; "
-                        "peak = best integer lane-instructions/s measured on this GPU in this run: independent LOP3 (alu pipe) + IMAD (fma pipe) "
-                        "streams, or the tile kernel's inner loop in isolation (max of vapor_gpu_int_peak(3), (4)); one instruction per "
-                        "test is the floor, so frac <= 30/32 for this loop; the kernel is integer-issue bound, HBM and tensor cores are idle by design",
-                "peak_alu_pipe_only_gops": alu_peak / 1e9, "peak_dual_pipe_gops": dual_peak / 1e9,
-                "nominal_issue_gops": nominal / 1e9,
-                "frac_of_nominal_issue": achieved / nominal,
-                "launches_per_step": int(tm_last["n_waves"]), "algorithmic_ops_per_launch": tm_last["cells"] * ops_per_cell / max(1, tm_last["n_waves"]),
-                "share_of_step": tile_ms / max(dev_ms, 1e-9)}
-    roofline_hbm = {"kernel": "k1_pack_kmers", "bound": "hbm", "achieved": pack_bytes / pack_s / 1e9 if pack_s > 0 else None,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": (pack_bytes / pack_s / 1e9 / hbm_peak) if pack_s > 0 else None,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                    "share_of_step": pack_ms / max(dev_ms, 1e-9)}
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    K = args.steps
+    n_waves = max(1, int(tm_last["n_waves"]))
+    mode = int(tm_last["k2_mode"])
+    nominal = 148 * 128 * 1.965e9                              # 4 SMSPs x 1 warp instruction/clk x 32 lanes at 1965 MHz
+    kernels = {}
+    # kernel 1: 1 B/base read + 0.25 B/base of 2-bit code = SURVEY 8(d)'s algorithmic 1.25 B/base; what it really moves is
+    # 1 B read + 1 B code + 4 B word per base
+    pack_s = acc["pack_ms"] * 1e-3 / K
+    if pack_s > 0:
+        kernels["k1_pack_kmers"] = {"bound": "hbm", "ms": 1e3 * pack_s, "algorithmic_bytes": 1.25 * tm_last["bases"], "actual_bytes": 6.0 * tm_last["bases"],
+                                    "achieved": 1.25 * tm_last["bases"] / pack_s / 1e9, "achieved_actual_bytes": 6.0 * tm_last["bases"] / pack_s / 1e9,
+                                    "peak": hbm_peak, "unit": "GB/s", "frac": 1.25 * tm_last["bases"] / pack_s / 1e9 / hbm_peak,
+                                    "frac_actual_bytes": 6.0 * tm_last["bases"] / pack_s / 1e9 / hbm_peak}
+    tile_s = acc["tile_ms"] * 1e-3 / K
+    k_arr = batch.task_k.astype(np.int64)
+    if mode == 0:
+        ops_per_cell = float(np.mean((2 * k_arr + 31) // 32)) if int(k_arr.max(initial=10)) <= 15 else 1.0
+        int_peak = max(eng.int_peak(3), eng.int_peak(1), eng.int_peak(2))
+        ach = tm_last["cells"] * ops_per_cell / tile_s
+        kernels["k2_tile_match"] = {"bound": "int32_issue", "ms": 1e3 * tile_s, "achieved": ach / 1e9, "peak": nominal / 1e9, "unit": "Gop/s",
+                                    "frac": ach / nominal, "peak_source": "nominal issue limit 148 SM x 128 lanes x 1.965 GHz",
+                                    "frac_of_measured_lop3_imad_streams": ach / int_peak, "measured_lop3_imad_gops": int_peak / 1e9,
+                                    "ops": "one 32-bit word compare per cell (k <= 15: exact canonical word; k > 15: hashed word, confirmed only on a match)",
+                                    "padded_cells": int(tm_last["padded_cells"]), "launches_per_step": n_waves}
+    else:
+        # join kernel: per launch it must read every plot's read words once (4 B), every table once and write the hits (8 B)
+        n_words = float(tm_last["probe_words"])
+        table_bytes = float(tm_last["table_bytes"])
+        alg = 4.0 * n_words + table_bytes + 8.0 * tm_last["hits"]
+        kernels["k2_join_match"] = {"bound": "hbm", "ms": 1e3 * tile_s, "algorithmic_bytes": alg, "achieved": alg / tile_s / 1e9, "peak": hbm_peak,
+                                    "unit": "GB/s", "frac": alg / tile_s / 1e9 / hbm_peak,
+                                    "cells_nominal": int(tm_last["cells"]), "cells_evaluated": int(tm_last["evaluated_cells"]),
+                                    "evaluated_cells_per_s": tm_last["evaluated_cells"] / tile_s,
+                                    "read_words_probed_per_s": n_words / tile_s,
+                                    "note": "radix-partitioned join: a read k-mer is compared only with the table bucket it falls into; the kernel is "
+                                            "bound by instruction issue and shared-memory latency of the probe loop, not by HBM or the compare count"}
+        table_s = tm_last["table_ms"] * 1e-3
+        if table_s > 0:
+            alg1b = table_bytes * 10.0 / 6.0            # 4 B/word read + 6 B/word (+ offsets) written
+            kernels["k1b_build_tables"] = {"bound": "hbm", "ms": 1e3 * table_s, "algorithmic_bytes": alg1b,
+                                           "achieved": alg1b / table_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                           "frac": alg1b / table_s / 1e9 / hbm_peak}
+    score_s = acc["score_ms"] * 1e-3 / K
+    if score_s > 0:
+        alg3 = 8.0 * tm_last["hits"] + 77.0 * batch.n_task
+        kernels["k3_score_reads"] = {"bound": "hbm", "ms": 1e3 * score_s, "algorithmic_bytes": alg3, "achieved": alg3 / score_s / 1e9, "peak": hbm_peak,
+                                     "unit": "GB/s", "frac": alg3 / score_s / 1e9 / hbm_peak,
+                                     "note": "reads every hit once (8 B) and writes 77 B per read; latency-bound on short phases per read"}
+    dom = max(kernels, key=lambda n: kernels[n]["ms"])
+    step_ms = acc["total_ms"] / K
+    roofline = dict(kernels[dom])
+    roofline.update({"kernel": dom, "share_of_step": kernels[dom]["ms"] / max(step_ms, 1e-9), "peak_source": kernels[dom].get("peak_source", hbm_src),
+                     "traffic": None, "traffic_note": "per-launch DRAM bytes from ncu are in profiles/ (captured at a smaller batch)"})
+    if roofline["bound"] != "hbm":
+        roofline["bound_schema"] = "integer issue (the schema's hbm|tensor does not apply: integer compare work)"
 
     # ---- CPU baseline on rank 0 at N=1 ----------------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         impl, kind = _cpu_impl()
-        n_sample = args.ref_svs if args.ref_svs > 0 else max(4, min(2 * cores, 256))
-        n_sample = min(n_sample, n_sv)
-        sub = w.batch.shard(range(n_sample))
+        budget_cells = args.ref_seconds * 3 * cores * 2.5e8
+        my_costs = multi.sv_costs(w.batch)
+        n_sample = args.ref_svs if args.ref_svs > 0 else int(max(4, min(w.batch.n_sv, budget_cells / max(1.0, float(my_costs.mean())))))
+        ids = stratified_ids(my_costs, n_sample)
+        sub = w.batch.shard(ids)
         pool = _make_pool(cores)
         dt, cpu_scores = cpu_score_sample(sub, cores, pool)
         if pool is not None:
             pool.close()
         # the sample doubles as a parity spot check of the timed GPU results
+        tix = multi.part_task_index(w.batch.sv_task_off, ids)
         ok = True
-        for t, sc in enumerate(cpu_scores):
+        for t, sc in zip(tix, cpu_scores):
             g_ok = res.task_status[t] == 1
             if (sc is None) != (not g_ok) or (sc is not None and abs(sc - res.task_score[t]) > 1e-5):
                 ok = False
         cpu_baseline = {"value": sub.n_task / dt, "unit": UNIT, "cores": cores, "kind": kind,
-                        "sample": f"first {n_sample} SVs ({sub.n_task} reads) of the benchmark SV list, one pass, per-read tasks over a "
-                                  f"{cores}-process pool, {getattr(impl, '__vapor_kind__', 'numpy-oracle')}",
+                        "sample": f"{n_sample} SVs ({sub.n_task} reads) spread evenly over the benchmark SV list ordered by cost, one pass "
+                                  f"({dt:.1f} s), per-read tasks over a {cores}-process pool, {getattr(impl, '__vapor_kind__', 'numpy-oracle')}",
                         "gpu_scores_match_on_sample": ok}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic", "config": _config(n_sv),
-            "workload_stats": {"reads": int(total_reads), "cells": int(total_cells), "sequence_bytes_per_gpu": int(w.batch.seq_bytes.nbytes)},
-            "cells_per_sec": total_cells * args.steps / dev_s,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic", "config": _config_json(args, c, world),
+            "workload_stats": {"svs": int(n_list), "reads": int(total_reads), "cells": int(total_cells),
+                               "sequence_bytes_rank0": int(w.batch.seq_bytes.nbytes)},
+            "cells_per_sec_nominal": total_cells * args.steps / dev_s,
+            "cells_evaluated_per_sec": total_eval * args.steps / dev_s,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(batch.h2d_bytes()),
                     "d2h_bytes_per_step": int(res.d2h_bytes()), "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "api": "vapor_b200.engine.Pipeline(depth=2).map: two handles, each step = vapor_gpu_score on pinned host buffers",
+                    "api": "vapor_b200.engine.Pipeline(depth=2).map: two handles, each step = vapor_gpu_score on pinned host buffers, then "
+                           "multi.scatter_part into the shared input-order result arrays (N > 1)",
+                    "bytes_are": "per rank (rank 0)",
                     "single_blocking_call": {"value": total_reads * args.steps / e2e_single_s, "ms_per_step": 1e3 * e2e_single_s / args.steps,
                                              "host_prep_ms": tm_e2e["host_prep_ms"], "h2d_ms": tm_e2e["h2d_ms"], "d2h_ms": tm_e2e["d2h_ms"]}},
             "gpu_launches": int(launches_total),
-            "roofline": roofline, "roofline_hbm": roofline_hbm,
+            "output_checksum": checksum,
+            "partition": {"parts": world, "cells_max_over_mean": float(part_cells.max() / max(part_cells.mean(), 1.0)),
+                          "rule": "identity" if world == 1 else ("contiguous blocks (--weak)" if args.weak else "multi.partition_svs: greedy LPT on cells per SV")},
+            "roofline": roofline, "kernels": kernels,
             "cpu_baseline": cpu_baseline,
-            "phase_ms_per_step": {"pack": pack_ms / args.steps, "table": tm_last["table_ms"], "tile": tile_ms / args.steps, "score": score_ms / args.steps,
-                                  "genotype": geno_ms / args.steps},
+            "phase_ms_per_step": {"pack": acc["pack_ms"] / K, "table": acc["table_ms"] / K, "tile": acc["tile_ms"] / K,
+                                  "score": acc["score_ms"] / K, "genotype": acc["genotype_ms"] / K},
             "wall_ms_per_step_resident": 1e3 * wall_resident / args.steps,
-            "hits_per_step": int(tm_last["hits"]), "workload_gen_s": t_gen,
-            "k2_mode": int(tm_last["k2_mode"]), "evaluated_cells": int(tm_last["evaluated_cells"]),
-            "tile_padding": {"cells": int(tm_last["cells"]), "padded_cells": int(tm_last["padded_cells"]),
-                             "useful_frac": tm_last["cells"] / max(1, tm_last["padded_cells"])},
-            "sv_called": {"gt_0/0": int((res.sv_gt == 0).sum()), "gt_0/1": int((res.sv_gt == 1).sum()),
-                          "gt_1/1": int((res.sv_gt == 2).sum()), "NA": int((res.sv_gt == 255).sum())},
+            "hits_per_step_rank0": int(tm_last["hits"]), "workload_gen_s": t_gen,
+            "k2_mode": mode, "n_waves_rank0": n_waves, "overflow_plots_rank0": int(tm_last["n_overflow_plots"]),
+            "sv_called": {"gt_0/0": int((gathered.sv_gt == 0).sum()), "gt_0/1": int((gathered.sv_gt == 1).sum()),
+                          "gt_1/1": int((gathered.sv_gt == 2).sum()), "NA": int((gathered.sv_gt == 255).sum())},
         }
         _emit(line)
     eng.close()
     if dist is not None:
         dist.barrier()
+    if shared is not None:
+        shared.close()
+    if dist is not None:
         dist.destroy_process_group()
 
 
@@ -438,8 +591,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n-sv", type=int, default=N_SV_DEFAULT, help="SVs per GPU")
-    ap.add_argument("--ref-svs", type=int, default=0, help="SVs in the CPU sample (0 = 2 x host cores, capped at 256)")
+    ap.add_argument("--config", type=int, default=5, choices=sorted(CONFIGS), help="BASELINE.json workload (see the module docstring)")
+    ap.add_argument("--n-sv", type=int, default=0, help="SVs in the list (0 = the config's size); per GPU with --weak")
+    ap.add_argument("--weak", action="store_true", help="every rank scores its own --n-sv SVs instead of a share of one list")
+    ap.add_argument("--ref-svs", type=int, default=0, help="SVs per CPU sample (0 = sized from --ref-seconds)")
+    ap.add_argument("--ref-seconds", type=float, default=4.0, help="all-core seconds one reference-arm step should take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tile-variant", type=int, default=-1, help="tile-kernel inner loop (-1 = library default)")
     ap.add_argument("--k2-mode", type=int, default=-1, help="kernel 2: 1 = join (library default), 0 = all-pairs tile kernel")

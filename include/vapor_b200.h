@@ -107,6 +107,8 @@ typedef struct vapor_timings {
                                     kernel the sum over read k-mers of the size of the table bucket they fall into */
     float   table_ms;            /* kernel 1b: sorted word tables of the structure-side operands (k2_mode 1) */
     int32_t k2_mode;             /* kernel-2 variant the last plan was made for */
+    int64_t table_bytes;         /* bytes of the sorted word tables kernel 1b writes and the join kernel stages (k2_mode 1) */
+    int64_t probe_words;         /* read k-mer words the join kernel streams: sum of n over the non-empty plots */
 } vapor_timings_t;
 
 /* Open one handle on CUDA device `device`.  One handle per device/thread; a handle is

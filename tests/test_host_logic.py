@@ -94,6 +94,109 @@ def test_distributed_world2_gloo():
         assert np.array_equal(getattr(whole, f), got[f]), f
 
 
+def _strong_worker(rank, world, port, tag, q):
+    """What bench.py does per rank under torchrun (strong scaling), with the CPU oracle standing in for the GPU."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    kw = dict(seed=31, recipe="complex", size_range=(200, 700), reads_per_sv=3)
+    n_list = 9
+    costs, ntask = synth.workload_costs(n_list, with_tasks=True, **kw)
+    parts = multi.partition_svs(costs, world)
+    mine = parts[rank]
+    w = synth.make_workload(0, sv_ids=mine, **kw)
+    sv_task_off = np.concatenate([[0], np.cumsum(ntask)])
+    shared = multi.SharedResults(tag, int(sv_task_off[-1]), n_list, create=True) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        shared = multi.SharedResults(tag, int(sv_task_off[-1]), n_list, create=False)
+    multi.scatter_part(shared.results, multi.part_task_index(sv_task_off, mine), mine, _oracle_scorer(w.batch))
+    dist.barrier()
+    if rank == 0:
+        q.put({f: np.array(getattr(shared.results, f)) for f in shared.results.__dataclass_fields__})
+    dist.barrier()
+    shared.close()
+    dist.destroy_process_group()
+
+
+def test_strong_scaling_world2_shared_gather():
+    """world_size 2 over gloo on CPU: every rank derives the same LPT partition from costs that need no sequence,
+    builds and scores only its part, and writes it to its input positions in /dev/shm arrays; rank 0 then holds the
+    whole list in input order -- identical (same bench.output_checksum) to scoring the list in one piece."""
+    import torch.multiprocessing as mp
+    import bench
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29300 + os.getpid() % 300
+    tag = f"test_{os.getpid()}"
+    procs = [ctx.Process(target=_strong_worker, args=(r, 2, port, tag, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    whole_w = synth.make_workload(9, seed=31, recipe="complex", size_range=(200, 700), reads_per_sv=3)
+    whole = _oracle_scorer(whole_w.batch)
+    for f in whole.__dataclass_fields__:
+        assert np.array_equal(getattr(whole, f), got[f]), f
+    assert bench.output_checksum(whole) == bench.output_checksum(Results(**got))
+    assert not [f for f in os.listdir("/dev/shm") if tag in f]                  # the owner removed the shared arrays
+
+
+def test_costs_without_sequences_match_generated_workloads():
+    """synth.workload_costs (used to partition a 100k-SV list before any rank builds its share) equals the cells of
+    the generated tasks, for every recipe; an arbitrary subset of SV ids regenerates exactly those SVs."""
+    for recipe, kw in (("simple", dict(size_range=(50, 900))), ("complex", dict(size_range=(200, 900))),
+                       ("large", dict(size_range=(10000, 14000), k_choices=(10, 20, 30, 40)))):
+        n = 14 if recipe == "complex" else 6
+        w = synth.make_workload(n, seed=3, recipe=recipe, reads_per_sv=2, **kw)
+        costs, ntask = synth.workload_costs(n, 3, recipe=recipe, reads_per_sv=2, with_tasks=True, **kw)
+        assert np.array_equal(costs, multi.sv_costs(w.batch)), recipe
+        assert np.array_equal(ntask, np.diff(w.batch.sv_task_off)), recipe
+        ids = [2, 3, n - 1]
+        sub = synth.make_workload(0, seed=3, recipe=recipe, reads_per_sv=2, sv_ids=ids, **kw)
+        ref = w.batch.shard(ids)
+        assert np.array_equal(sub.batch.seq_bytes, ref.seq_bytes) and np.array_equal(sub.batch.task_alt, ref.task_alt), recipe
+
+
+def test_complex_recipe_shapes():
+    """Config 3 events: one task group per distinct alternative haplotype, the same reads against each; REDEF exactly
+    when a block repeats in the allele (Simple_function.pyx:1519-1523); junction fallbacks are 1 kb W10 windows."""
+    from vapor_b200.engine import MODE_REDEF
+    w = synth.make_workload(14, seed=11, recipe="complex", size_range=(300, 900), reads_per_sv=4)
+    off = w.batch.sv_task_off
+    lens = np.diff(w.batch.seq_off)
+    for s, kind in enumerate(w.sv_type):
+        alleles = synth.COMPLEX_KINDS[kind][1]
+        t = slice(off[s], off[s + 1])
+        assert off[s + 1] - off[s] == 4 * len(alleles), kind
+        assert len(set(w.batch.task_ref[t].tolist())) == 1 and len(set(w.batch.task_alt[t].tolist())) == len(alleles)
+        for a, al in enumerate(alleles):
+            ta = slice(off[s] + 4 * a, off[s] + 4 * a + 4)
+            assert np.array_equal(w.batch.task_read[ta], w.batch.task_read[off[s]:off[s] + 4])       # same reads for every allele
+            if kind == "JUNCTION":
+                assert set(w.batch.task_mode[ta].tolist()) == {MODE_W10} and lens[w.batch.task_ref[off[s]]] == 1001
+            else:
+                repeated = max(al.count(c) for c in al if c != "^") > 1
+                assert set(w.batch.task_mode[ta].tolist()) == {MODE_REDEF if repeated else MODE_ABS}, (kind, al)
+    # reads drawn from the planted haplotypes score: most het / hom-alt events get a non-0/0 call from the oracle
+    exp = BO.score_batch(w.batch, with_hits=False)
+    called = [(g, int(c)) for g, c in zip(w.sv_genotype, exp["sv_gt"]) if g > 0]
+    assert sum(1 for g, c in called if c in (1, 2)) >= 0.7 * len(called)
+
+
+def test_stratified_sample_covers_types_and_sizes():
+    import bench
+    costs = synth.workload_costs(400, 5)
+    ids = bench.stratified_ids(costs, 40)
+    assert len(set(ids.tolist())) == 40
+    assert len({i % 4 for i in ids}) == 4                                          # all four SV types
+    q = np.quantile(costs, [0.25, 0.75])
+    assert (costs[ids] < q[0]).any() and (costs[ids] > q[1]).any()
+    assert not set(ids.tolist()) & set(bench.stratified_ids(costs, 40, offset=1).tolist())
+
+
 def test_bam_in_decide_patterns(tmp_path):
     """One file, or every file of the directory matching an XXX / * pattern (Simple_function.pyx:69-89)."""
     from vapor_b200 import Simple_function as SF

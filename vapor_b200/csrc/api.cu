@@ -479,6 +479,8 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
     h->tm.n_strips = h->plan_mode == 0 ? h->strip_prefix.back() : (int64_t)h->jp.items.size();
     h->tm.n_waves = (int64_t)h->waves.size(); h->tm.bases = bases;
     h->tm.k2_mode = h->plan_mode;
+    h->tm.table_bytes = h->table_bytes;
+    { int64_t pw = 0; for (const Plot& p : h->plots) if (p.n > 0 && p.m > 0) pw += p.n; h->tm.probe_words = pw; }
     return VAPOR_OK;
 }
 

@@ -370,8 +370,10 @@ class Pipeline:
     def __enter__(self): return self
     def __exit__(self, *a): self.close()
 
-    def map(self, batches, results: Optional[Sequence[Optional[Results]]] = None):
-        """Score every batch; ``results[i]`` (optional) is a caller-provided (e.g. pinned) Results to fill."""
+    def map(self, batches, results: Optional[Sequence[Optional[Results]]] = None, after=None):
+        """Score every batch; ``results[i]`` (optional) is a caller-provided (e.g. pinned) Results to fill.
+        ``after(results_i)`` (optional) runs in the worker thread right after batch i was scored -- e.g. the scatter
+        of a shard's results into shared input-order arrays -- while the other handle keeps the GPU busy."""
         import queue
         import threading
         batches = list(batches)
@@ -391,6 +393,8 @@ class Pipeline:
                 try:
                     into = results[i] if results is not None and results[i] is not None else _alloc_results(batches[i].n_task, batches[i].n_sv)
                     out[i] = eng.score_into(batches[i], into)
+                    if after is not None:
+                        after(out[i])
                 except BaseException as e:          # noqa: BLE001
                     errs.append(e)
                     return

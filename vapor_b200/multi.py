@@ -40,21 +40,70 @@ def partition_svs(costs: Sequence[int], n_parts: int) -> List[np.ndarray]:
     return [np.array(sorted(p), dtype=np.int64) for p in parts]
 
 
+def part_task_index(sv_task_off: np.ndarray, sv_ids: np.ndarray) -> np.ndarray:
+    """Input positions of the tasks of the SVs ``sv_ids`` (in that order) in the whole list."""
+    sv_ids = np.asarray(sv_ids, dtype=np.int64)
+    t0, t1 = sv_task_off[sv_ids], sv_task_off[sv_ids + 1]
+    cnt = t1 - t0
+    loc = np.zeros(len(sv_ids) + 1, dtype=np.int64)
+    np.cumsum(cnt, out=loc[1:])
+    return np.repeat(t0 - loc[:-1], cnt) + np.arange(loc[-1])
+
+
+def scatter_part(out: Results, tix: np.ndarray, sv_ids: np.ndarray, part: Results) -> None:
+    """Write one part's results to their input positions in ``out`` (pre-sized arrays of the whole list)."""
+    if len(sv_ids) == 0:
+        return
+    for f in ("task_score", "task_status", "task_stat", "task_hits", "task_hitsum"):
+        getattr(out, f)[tix] = getattr(part, f)
+    for f in ("sv_qs", "sv_gs", "sv_gq", "sv_gt", "sv_nscore"):
+        getattr(out, f)[sv_ids] = getattr(part, f)
+
+
 def merge_results(batch: PackedBatch, parts: Sequence[np.ndarray], results: Sequence[Results]) -> Results:
     """Scatter per-part results back to input order."""
     out = _alloc_results(batch.n_task, batch.n_sv)
     for sv_ids, r in zip(parts, results):
-        if len(sv_ids) == 0:
-            continue
-        t0, t1 = batch.sv_task_off[sv_ids], batch.sv_task_off[sv_ids + 1]
-        cnt = t1 - t0
-        loc = np.concatenate([[0], np.cumsum(cnt)])
-        tix = np.repeat(t0 - loc[:-1], cnt) + np.arange(loc[-1])
-        for f in ("task_score", "task_status", "task_stat", "task_hits", "task_hitsum"):
-            getattr(out, f)[tix] = getattr(r, f)
-        for f in ("sv_qs", "sv_gs", "sv_gq", "sv_gt", "sv_nscore"):
-            getattr(out, f)[sv_ids] = getattr(r, f)
+        if len(sv_ids):
+            scatter_part(out, part_task_index(batch.sv_task_off, sv_ids), np.asarray(sv_ids, dtype=np.int64), r)
     return out
+
+
+class SharedResults:
+    """The result arrays of a whole SV list in shared host memory (files under /dev/shm mapped by every process):
+    the pre-sized host arrays indexed by input position of SURVEY.md 8(e).  One process per GPU scores its part
+    and writes it straight to its input positions (``scatter_part``); after a barrier the owner (rank 0) holds
+    the gathered results in input order.  No collective, no pickling, no copy through a socket."""
+
+    SPEC = (("task_score", np.float64, 1), ("task_status", np.uint8, 1), ("task_stat", np.float64, 4),
+            ("task_hits", np.uint32, 4), ("task_hitsum", np.uint64, 4), ("sv_qs", np.float64, 0),
+            ("sv_gs", np.float64, 0), ("sv_gq", np.float64, 0), ("sv_gt", np.uint8, 0), ("sv_nscore", np.int32, 0))
+
+    def __init__(self, tag: str, n_task: int, n_sv: int, create: bool, directory: Optional[str] = None):
+        import os
+        import tempfile
+        d = directory or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
+        self.paths, arrs = [], {}
+        for name, dt, width in self.SPEC:
+            n = n_task if name.startswith("task_") else n_sv
+            shape = (n, width) if width > 1 else (n,)
+            path = os.path.join(d, f"vapor_b200_{tag}_{name}.bin")
+            self.paths.append(path)
+            arrs[name] = np.memmap(path, dtype=dt, mode="w+" if create else "r+", shape=shape) if n else np.zeros(shape, dt)
+        if create and n_sv:
+            arrs["sv_gt"][:] = 255
+        self.results = Results(**arrs)
+        self.owner = create
+
+    def close(self):
+        import os
+        self.results = None
+        if self.owner:
+            for p in self.paths:
+                try:
+                    os.unlink(p)
+                except OSError:
+                    pass
 
 
 def score_sharded(batch: PackedBatch, scorers: Sequence[Callable[[PackedBatch], Results]]) -> Results:
