@@ -542,8 +542,9 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(batch.h2d_bytes()),
                     "d2h_bytes_per_step": int(res.d2h_bytes()), "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "api": "vapor_b200.engine.Pipeline(depth=2).map: two handles, each step = vapor_gpu_score on pinned host buffers, then "
-                           "multi.scatter_part into the shared input-order result arrays (N > 1)",
+                    "api": "vapor_b200.engine.Pipeline(depth=2).map: two handles, each step = vapor_gpu_upload + vapor_gpu_run + vapor_gpu_fetch on "
+                           "pinned host buffers (host planning + H2D + kernels + D2H every step, the steps of the two handles interleaved), "
+                           "then multi.scatter_part into the shared input-order result arrays (N > 1)",
                     "bytes_are": "per rank (rank 0)",
                     "single_blocking_call": {"value": total_reads * args.steps / e2e_single_s, "ms_per_step": 1e3 * e2e_single_s / args.steps,
                                              "host_prep_ms": tm_e2e["host_prep_ms"], "h2d_ms": tm_e2e["h2d_ms"], "d2h_ms": tm_e2e["d2h_ms"]}},

@@ -173,6 +173,13 @@ int vapor_gpu_summarize(void* handle, const double* scores, const int64_t* sv_of
 int vapor_gpu_host_alloc(void** p, int64_t bytes);
 int vapor_gpu_host_free(void* p);
 
+/* Host-side planning alone (operands, plots, waves, kernel-2 and kernel-3 work lists) -- no device is touched.
+ * For tests (the plan must not depend on the number of planning threads) and host-side tuning: *ms = wall time,
+ * *digest = FNV-1a over every plan array the kernels read, counts[8] = operands, plots, tasks, waves, table chunks,
+ * join items, recurrence cells, largest hit slab of a wave.  Any output pointer may be NULL. */
+int vapor_host_plan(const vapor_batch_t* in, int k2_mode, int threads, int64_t wave_budget_bytes,
+                    double* ms, uint64_t* digest, int64_t* counts);
+
 /* Integer-issue microbenchmark used as the roofline denominator of the tile kernel:
  * which = 0: 32-bit compare-accumulate (ISETP) lane-ops/s, 1: LOP3 lane-ops/s, 2: IADD3 lane-ops/s (alu pipe alone),
  * 3: independent LOP3 + IMAD streams (alu pipe + fma pipe together: the dual-pipe integer issue rate the tile

@@ -220,3 +220,21 @@ def test_small_helpers_match_reference_semantics():
     assert SF.block_around_check("ba", "ab") == [["-", "b"], ["b", "a"], ["a", "+"]]
     assert SF.minimize_pacbio_read_list([["r", i % 3, "q"] for i in range(30)])[:10] == [["r", 0, "q"]] * 10
     assert len(SF.minimize_pacbio_read_list([["r", i % 3, "q"] for i in range(30)])) == 20
+
+
+def test_host_plan_independent_of_thread_count():
+    """vapor_host_plan (no device needed): the plan digest -- operands, plots, tasks, waves, table chunks, join items,
+    kernel-3 class lists -- is the same for 1, 2, 3 and 7 planning threads, for both kernel-2 variants, with one wave
+    and with many."""
+    from vapor_b200.engine import host_plan
+    w = synth.make_workload(300, seed=41, size_range=(50, 1500), reads_per_sv=5, lowercase_every=7, max_miss=3)
+    for mode in (0, 1):
+        for budget in (0, 8 << 20):
+            base = host_plan(w.batch, mode, 1, budget)
+            assert base["tasks"] == w.batch.n_task and base["cells"] >= w.cells      # lower-case DEL structures add W10 plots
+            assert (base["waves"] > 3) == (budget > 0)
+            for th in (2, 3, 7):
+                got = host_plan(w.batch, mode, th, budget)
+                assert got["digest"] == base["digest"] and got["waves"] == base["waves"], (mode, budget, th)
+    cx = synth.make_workload(28, seed=5, recipe="complex", size_range=(200, 900), reads_per_sv=3)
+    assert host_plan(cx.batch, 1, 1)["digest"] == host_plan(cx.batch, 1, 4)["digest"]

@@ -22,7 +22,7 @@ EXPORTS = [
     "vapor_gpu_open", "vapor_gpu_close", "vapor_gpu_last_error", "vapor_gpu_set_hit_budget", "vapor_gpu_set_option",
     "vapor_gpu_score", "vapor_gpu_upload", "vapor_gpu_run", "vapor_gpu_fetch",
     "vapor_gpu_last_timings", "vapor_gpu_dotdata", "vapor_gpu_selfplot_qc", "vapor_gpu_summarize", "vapor_gpu_host_alloc", "vapor_gpu_host_free",
-    "vapor_gpu_int_peak", "vapor_hit_mix", "vapor_b200_abi_version", "vapor_gpu_device_count",
+    "vapor_gpu_int_peak", "vapor_host_plan", "vapor_hit_mix", "vapor_b200_abi_version", "vapor_gpu_device_count",
 ]
 
 
@@ -100,6 +100,7 @@ def load() -> C.CDLL:
     lib.vapor_gpu_host_alloc.argtypes = [C.POINTER(vp), i64]
     lib.vapor_gpu_host_free.argtypes = [vp]
     lib.vapor_gpu_int_peak.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    lib.vapor_host_plan.argtypes = [C.POINTER(vapor_batch_t), i32, i32, i64, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(i64)]
     lib.vapor_hit_mix.argtypes = [C.c_uint32, C.c_uint32]
     lib.vapor_hit_mix.restype = C.c_uint64
     lib.vapor_b200_abi_version.argtypes = []

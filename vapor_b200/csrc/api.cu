@@ -51,10 +51,15 @@ struct DevBuf {                      // grow-only device buffer
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// A wave = a run of whole SVs whose transient device data (k-mer words, codes, tables, hit lists) fits the budget.
+// Offsets inside Operand / TabChunk / Plot are relative to the wave's buffers, which the next wave reuses.
 struct Wave {
     int64_t task_begin, task_end;
     int64_t plot_begin, plot_end;
-    int64_t hit_elems;
+    int64_t op_begin, op_end;
+    int64_t chunk_begin, chunk_end;              // table chunks (join mode)
+    int64_t hit_elems, hash_elems, code_bytes, table_bytes;
+    int64_t bytes() const { return 8 * hit_elems + 4 * hash_elems + code_bytes + table_bytes; }
 };
 
 // kernel-3 scratch classes: bins that fit in shared memory, then a global-memory fallback
@@ -72,6 +77,7 @@ struct JoinPlan {
     std::vector<int32_t> jplots;                 // plot ids, grouped by structure operand
 };
 
+struct PlanShard;
 struct Handle {
     int device = 0;
     int sm_count = 148;
@@ -95,6 +101,9 @@ struct Handle {
     std::vector<int32_t> chunk_prefix;
     std::vector<int64_t> strip_prefix;
     std::vector<Wave> waves;
+    std::vector<int64_t> group_off;              // [n_groups+1] task ranges of the planning groups (SVs)
+    std::vector<PlanShard>* shards = nullptr;    // planner scratch, kept between calls (capacity reuse)
+    ~Handle();
     std::vector<int32_t> class_ids;              // task ids grouped by (wave, class)
     std::vector<int64_t> class_off;              // [n_waves*K3_NCLASS+1]
     std::vector<TabChunk> chunks;                // join mode: table chunks of all structure-side operands
@@ -199,24 +208,32 @@ int k3_class_of(int nb) {
 // planning: operands (k-mer word arrays), plots, tasks, waves
 // ------------------------------------------------------------------------------------------
 
-// Table chunks of every structure-side operand (join kernel).  op_chunk0[i] = first chunk of operand i, or -1.
-int64_t build_chunks(const std::vector<Operand>& ops, std::vector<TabChunk>& chunks, std::vector<int32_t>& op_chunk0) {
+// Table chunks of every structure-side operand (join kernel), wave by wave: blob offsets restart in every wave.
+// op_chunk0[i] = first chunk of operand i, or -1.  Returns the largest table size of a wave.
+int64_t build_chunks(const std::vector<Operand>& ops, std::vector<Wave>& waves, std::vector<TabChunk>& chunks, std::vector<int32_t>& op_chunk0) {
     chunks.clear();
     op_chunk0.assign(ops.size(), -1);
-    int64_t off = 0;
-    for (size_t i = 0; i < ops.size(); ++i) {
-        const Operand& o = ops[i];
-        if (!(o.flags & OPF_TABLE) || o.n <= 0) continue;
-        op_chunk0[i] = (int32_t)chunks.size();
-        for (int p0 = 0; p0 < o.n; p0 += K2J_CH) {
-            TabChunk c{};
-            c.op = (int32_t)i; c.pos0 = p0; c.len = std::min(K2J_CH, o.n - p0); c.bits = k2j_bits(c.len);
-            c.blob_bytes = k2j_blob_bytes(c.len, c.bits); c.blob_off = off;
-            off += c.blob_bytes;
-            chunks.push_back(c);
+    int64_t worst = 0;
+    for (Wave& w : waves) {
+        int64_t off = 0;
+        w.chunk_begin = (int64_t)chunks.size();
+        for (int64_t i = w.op_begin; i < w.op_end; ++i) {
+            const Operand& o = ops[i];
+            if (!(o.flags & OPF_TABLE) || o.n <= 0) continue;
+            op_chunk0[i] = (int32_t)chunks.size();
+            for (int p0 = 0; p0 < o.n; p0 += K2J_CH) {
+                TabChunk c{};
+                c.op = (int32_t)i; c.pos0 = p0; c.len = std::min(K2J_CH, o.n - p0); c.bits = k2j_bits(c.len);
+                c.blob_bytes = k2j_blob_bytes(c.len, c.bits); c.blob_off = off;
+                off += c.blob_bytes;
+                chunks.push_back(c);
+            }
         }
+        w.chunk_end = (int64_t)chunks.size();
+        w.table_bytes = off;
+        worst = std::max(worst, off);
     }
-    return off;
+    return worst;
 }
 
 int k2j_class_of(int blob_bytes) {
@@ -281,6 +298,245 @@ void build_join_items(const std::vector<Plot>& plots, const std::vector<Wave>& w
     }
 }
 
+// ---- the batch planner ---------------------------------------------------------------------------------------
+// Groups = SVs (or runs of 64 tasks when the batch has no SV table).  Everything a group needs -- its operands (one
+// per distinct (sequence, k, casing, role)), plots, tasks, table chunks, join items -- is local to the group, so the
+// plan is made in three phases:
+//   A (parallel over contiguous group ranges): each shard builds its groups' records with group-relative ids/offsets;
+//   B (serial, O(groups)): waves are cut at group boundaries by the memory budget, every group gets its bases;
+//   C (parallel): the records are copied to their final places with the bases added.
+// The result does not depend on the number of threads (tests/test_host_logic.py pins the digest).
+struct GroupSize {
+    int32_t n_ops, n_plots, n_tasks, n_chunks, n_jplots, n_k1chunks;
+    int32_t n_items[K2J_NCLASS];
+    int32_t n_cls[K3_NCLASS];
+    int64_t n_strips;
+    int64_t hash_elems, code_bytes, table_bytes, hit_elems;
+};
+struct GroupBase {
+    int64_t op, plot, chunk, jplot, k1chunk, strip;
+    int64_t hash, code, table, hit;
+    int64_t item[K2J_NCLASS];
+    int64_t cls[K3_NCLASS];
+};
+struct PlanShard {
+    int64_t g0 = 0, g1 = 0;
+    std::vector<Operand> ops; std::vector<Plot> plots; std::vector<Task> tasks; std::vector<TabChunk> chunks;
+    std::vector<JoinItem> items; std::vector<uint8_t> item_class; std::vector<int32_t> jplots;
+    std::vector<uint8_t> task_class; std::vector<int32_t> k1chunks; std::vector<int32_t> strips;
+    int64_t cells = 0, padded_cells = 0, bases = 0, probe_words = 0;
+    int max_nb = 1;
+    int rc = VAPOR_OK; std::string err;
+};
+
+Handle::~Handle() { delete shards; }
+
+void plan_shard(const Handle* h, const vapor_batch_t* in, const std::vector<int64_t>& goff, PlanShard& sh, std::vector<GroupSize>& gsize) {
+    const int64_t n_seq = in->n_seq;
+    const int mode_k2 = h->k2_mode;
+    const int rows = k2_variant_rows(h->tile_variant);
+    struct Key { int32_t seq, k, flags, op; };
+    std::vector<Key> local;                      // operand cache of the current group
+    std::vector<std::pair<int32_t, int8_t>> lower;   // has-lower-case memo of the current group's structure sequences
+    std::vector<int32_t> op_chunk0, members;
+    auto fail = [&](const char* msg) { sh.rc = VAPOR_E_ARG; sh.err = msg; };
+    for (int64_t g = sh.g0; g < sh.g1 && sh.rc == VAPOR_OK; ++g) {
+        GroupSize gs{};
+        local.clear(); lower.clear();
+        const size_t op0 = sh.ops.size(), plot0 = sh.plots.size();
+        auto seq_has_lower = [&](int32_t s) -> bool {
+            for (auto& e : lower) if (e.first == s) return e.second != 0;
+            const uint8_t* p = in->seq_bytes + in->seq_off[s];
+            const int64_t L = in->seq_off[s + 1] - in->seq_off[s];
+            int8_t f = 0;
+            int64_t i = 0;
+            // ASCII lower-case letters have bit 5 set, upper-case ones do not: skip 8 bytes at a time while no byte has it
+            for (; i + 8 <= L; i += 8) {
+                uint64_t w8; memcpy(&w8, p + i, 8);
+                if (w8 & 0x2020202020202020ull) {
+                    for (int j = 0; j < 8; ++j) if (p[i + j] >= 'a' && p[i + j] <= 'z') { f = 1; break; }
+                    if (f) break;
+                }
+            }
+            for (; !f && i < L; ++i) if (p[i] >= 'a' && p[i] <= 'z') f = 1;
+            lower.push_back({s, f});
+            return f != 0;
+        };
+        auto get_op = [&](int32_t seq, int k, int flags) -> int32_t {
+            for (auto& e : local) if (e.seq == seq && e.k == k && e.flags == flags) return e.op;
+            Operand o{};
+            o.seq_begin = in->seq_off[seq];
+            o.len = (int32_t)(in->seq_off[seq + 1] - in->seq_off[seq]);
+            o.k = k; o.flags = flags;
+            o.n = std::max(0, o.len - k + 1);
+            o.hash_off = gs.hash_elems; o.code_off = gs.code_bytes;
+            gs.hash_elems += align4(o.n) + 8;
+            gs.code_bytes += (o.len + 8 + 15) & ~15;     // 16-byte aligned code strings (8-byte stores in kernel 1)
+            const int k1c = std::max(1, (o.len + K1_CHUNK - 1) / K1_CHUNK);
+            sh.k1chunks.push_back(k1c); gs.n_k1chunks += k1c;
+            sh.bases += o.len;
+            sh.ops.push_back(o);
+            const int32_t id = (int32_t)(sh.ops.size() - 1 - op0);
+            local.push_back({seq, k, flags, id});
+            return id;
+        };
+        auto add_plot = [&](int32_t rop, int32_t sop, int32_t miss_bp) -> int32_t {
+            const Operand& r = sh.ops[op0 + rop];
+            Operand& s = sh.ops[op0 + sop];
+            // the reference slices ref_seq[miss_bp:] (Simple_function.pyx:185-186): a negative miss_bp, which
+            // cigar2alignstart_by_pos can return, counts from the end of the string as Python slicing does
+            const int32_t miss = miss_bp >= 0 ? miss_bp : std::max(0, s.len + miss_bp);
+            Plot p{};
+            p.read_op = rop; p.struct_op = sop; p.miss = miss;
+            p.n = r.n;
+            p.m = (miss <= s.len) ? std::max(0, s.len - miss - s.k + 1) : 0;
+            p.cap = (p.n > 0 && p.m > 0) ? (uint32_t)align4((int64_t)p.n + p.m + 32) : 0u;
+            p.hit_off = gs.hit_elems;
+            gs.hit_elems += p.cap;
+            s.flags |= OPF_TABLE;
+            sh.max_nb = std::max(sh.max_nb, p.n + p.m - 1);
+            sh.cells += (int64_t)p.n * p.m;
+            if (p.n > 0 && p.m > 0) sh.probe_words += p.n;
+            int64_t ns = 0;
+            if (mode_k2 == 0) ns = cut_strips(p, rows, &sh.padded_cells);
+            sh.strips.push_back((int32_t)ns); gs.n_strips += ns;
+            sh.plots.push_back(p);
+            return (int32_t)(sh.plots.size() - 1 - plot0);
+        };
+        for (int64_t t = goff[g]; t < goff[g + 1]; ++t) {
+            const int32_t rs = in->task_read[t], fs = in->task_ref[t], as = in->task_alt[t];
+            const int32_t miss = in->task_miss[t];
+            const int k = in->task_k[t], mode = in->task_mode[t];
+            if (rs < 0 || rs >= n_seq || fs < 0 || fs >= n_seq || as < 0 || as >= n_seq) { fail("task sequence index out of range"); break; }
+            if (k < 1 || k > K1_MAXK) { fail("window_size k must be 1..40"); break; }
+            if (mode < 0 || mode > 3) { fail("unknown mode"); break; }
+            Task tk{};
+            tk.mode = mode;
+            tk.len_ref = (int32_t)(in->seq_off[fs + 1] - in->seq_off[fs]);
+            tk.len_alt = (int32_t)(in->seq_off[as + 1] - in->seq_off[as]);
+            tk.read_op = get_op(rs, k, OPF_READ);
+            const bool abs_first = (mode == VAPOR_MODE_ABS || mode == VAPOR_MODE_ABS_AND_W10);
+            const int fl_ref = (abs_first && seq_has_lower(fs)) ? OPF_UPPER : 0;
+            const int fl_alt = (abs_first && seq_has_lower(as)) ? OPF_UPPER : 0;
+            tk.plot[0] = add_plot(tk.read_op, get_op(fs, k, fl_ref), miss);
+            tk.plot[1] = add_plot(tk.read_op, get_op(as, k, fl_alt), miss);
+            tk.plot[2] = tk.plot[3] = -1;
+            if (mode == VAPOR_MODE_ABS_AND_W10) {       // W10 does not upper-case (Simple_function.pyx:277-279)
+                tk.plot[2] = fl_ref ? add_plot(tk.read_op, get_op(fs, k, 0), miss) : tk.plot[0];
+                tk.plot[3] = fl_alt ? add_plot(tk.read_op, get_op(as, k, 0), miss) : tk.plot[1];
+            }
+            int nb = 1;
+            for (int i = 0; i < 4; ++i) if (tk.plot[i] >= 0) { const Plot& p = sh.plots[plot0 + tk.plot[i]]; nb = std::max(nb, p.n + p.m - 1); }
+            const int cls = k3_class_of(nb);
+            sh.task_class.push_back((uint8_t)cls); ++gs.n_cls[cls];
+            sh.tasks.push_back(tk);
+        }
+        gs.n_ops = (int32_t)(sh.ops.size() - op0); gs.n_plots = (int32_t)(sh.plots.size() - plot0);
+        gs.n_tasks = (int32_t)(goff[g + 1] - goff[g]);
+        // join kernel: table chunks of the group's structure-side operands, then its items
+        if (mode_k2 == 1) {
+            op_chunk0.assign((size_t)gs.n_ops, -1);
+            for (int32_t o = 0; o < gs.n_ops; ++o) {
+                const Operand& op = sh.ops[op0 + o];
+                if (!(op.flags & OPF_TABLE) || op.n <= 0) continue;
+                op_chunk0[o] = gs.n_chunks;
+                for (int p0 = 0; p0 < op.n; p0 += K2J_CH) {
+                    TabChunk c{};
+                    c.op = o; c.pos0 = p0; c.len = std::min(K2J_CH, op.n - p0); c.bits = k2j_bits(c.len);
+                    c.blob_bytes = k2j_blob_bytes(c.len, c.bits); c.blob_off = gs.table_bytes;
+                    gs.table_bytes += c.blob_bytes;
+                    sh.chunks.push_back(c); ++gs.n_chunks;
+                }
+            }
+            const size_t chunk0 = sh.chunks.size() - (size_t)gs.n_chunks;
+            for (int32_t o = 0; o < gs.n_ops; ++o) {
+                if (op_chunk0[o] < 0) continue;
+                members.clear();                                   // plots on this table, in task order
+                for (int32_t q = 0; q < gs.n_plots; ++q) { const Plot& p = sh.plots[plot0 + q]; if (p.struct_op == o && p.n > 0 && p.m > 0) members.push_back(q); }
+                if (members.empty()) continue;
+                const int32_t jbase = gs.n_jplots;
+                sh.jplots.insert(sh.jplots.end(), members.begin(), members.end());
+                gs.n_jplots += (int32_t)members.size();
+                for (int32_t c = op_chunk0[o]; c < gs.n_chunks && sh.chunks[chunk0 + c].op == o; ++c) {
+                    const int kc = k2j_class_of(sh.chunks[chunk0 + c].blob_bytes);
+                    // runs of plots of about K2J_WORDS_PER_ITEM read words (at most K2J_PLOTS_PER_ITEM plots): items of similar length
+                    int32_t a = 0;
+                    const int32_t nm = (int32_t)members.size();
+                    while (a < nm) {
+                        int32_t e = a; int64_t words = 0;
+                        while (e < nm && e - a < K2J_PLOTS_PER_ITEM && (e == a || words + sh.plots[plot0 + members[e]].n <= K2J_WORDS_PER_ITEM)) {
+                            words += sh.plots[plot0 + members[e]].n; ++e;
+                        }
+                        sh.items.push_back(JoinItem{c, jbase + a, jbase + e, 0});
+                        sh.item_class.push_back((uint8_t)kc); ++gs.n_items[kc];
+                        a = e;
+                    }
+                }
+            }
+        }
+        gsize[(size_t)g] = gs;
+    }
+}
+
+void place_shard(Handle* h, const PlanShard& sh, const std::vector<GroupSize>& gsize, const std::vector<GroupBase>& gbase) {
+    size_t io = 0, ip = 0, it = 0, ic = 0, ii = 0, ij = 0;             // cursors into the shard's records
+    for (int64_t g = sh.g0; g < sh.g1; ++g) {
+        const GroupSize& gs = gsize[(size_t)g];
+        const GroupBase& gb = gbase[(size_t)g];
+        int32_t k1run = (int32_t)gb.k1chunk;
+        for (int32_t o = 0; o < gs.n_ops; ++o, ++io) {
+            Operand op = sh.ops[io];
+            op.hash_off += gb.hash; op.code_off += gb.code;
+            h->ops[(size_t)gb.op + o] = op;
+            h->chunk_prefix[(size_t)gb.op + o] = k1run;
+            k1run += sh.k1chunks[io];
+        }
+        int64_t srun = gb.strip;
+        for (int32_t q = 0; q < gs.n_plots; ++q, ++ip) {
+            Plot p = sh.plots[ip];
+            p.read_op += (int32_t)gb.op; p.struct_op += (int32_t)gb.op; p.hit_off += gb.hit;
+            h->plots[(size_t)gb.plot + q] = p;
+            srun += sh.strips[ip];
+            h->strip_prefix[(size_t)gb.plot + q + 1] = srun;
+        }
+        int64_t cls_run[K3_NCLASS];
+        for (int c = 0; c < K3_NCLASS; ++c) cls_run[c] = gb.cls[c];
+        const int64_t task0 = h->group_off[(size_t)g];
+        for (int32_t t = 0; t < gs.n_tasks; ++t, ++it) {
+            Task tk = sh.tasks[it];
+            for (int i = 0; i < 4; ++i) if (tk.plot[i] >= 0) tk.plot[i] += (int32_t)gb.plot;
+            tk.read_op += (int32_t)gb.op;
+            h->tasks[(size_t)task0 + t] = tk;
+            h->class_ids[(size_t)cls_run[sh.task_class[it]]++] = (int32_t)(task0 + t);
+        }
+        for (int32_t c = 0; c < gs.n_chunks; ++c, ++ic) {
+            TabChunk ch = sh.chunks[ic];
+            ch.op += (int32_t)gb.op; ch.blob_off += gb.table;
+            h->chunks[(size_t)gb.chunk + c] = ch;
+        }
+        for (int32_t j = 0; j < gs.n_jplots; ++j, ++ij) h->jp.jplots[(size_t)gb.jplot + j] = sh.jplots[ij] + (int32_t)gb.plot;
+        int64_t item_run[K2J_NCLASS];
+        for (int c = 0; c < K2J_NCLASS; ++c) item_run[c] = gb.item[c];
+        int32_t n_it = 0;
+        for (int c = 0; c < K2J_NCLASS; ++c) n_it += gs.n_items[c];
+        for (int32_t x = 0; x < n_it; ++x, ++ii) {
+            JoinItem item = sh.items[ii];
+            item.chunk += (int32_t)gb.chunk; item.jp_begin += (int32_t)gb.jplot; item.jp_end += (int32_t)gb.jplot;
+            h->jp.items[(size_t)item_run[sh.item_class[ii]]++] = item;
+        }
+    }
+}
+
+template <typename F>
+void run_threads(int n, F&& f) {
+    if (n <= 1) { f(0); return; }
+    std::vector<std::thread> th;
+    th.reserve((size_t)n - 1);
+    for (int i = 1; i < n; ++i) th.emplace_back([&f, i]() { f(i); });
+    f(0);
+    for (auto& t : th) t.join();
+}
+
 int plan_batch(Handle* h, const vapor_batch_t* in) {
     if (!in || !in->seq_off || (!in->seq_bytes && in->n_seq > 0 && in->seq_off[in->n_seq] > 0)) { h->err = "NULL batch arrays"; return VAPOR_E_ARG; }
     if (in->n_task > 0 && (!in->task_read || !in->task_ref || !in->task_alt || !in->task_miss || !in->task_k || !in->task_mode)) {
@@ -296,191 +552,141 @@ int plan_batch(Handle* h, const vapor_batch_t* in) {
     for (int64_t s = 0; s < n_sv; ++s)
         if (in->sv_task_off[s + 1] < in->sv_task_off[s]) { h->err = "sv_task_off must be non-decreasing"; return VAPOR_E_ARG; }
 
-    h->ops.clear(); h->plots.clear(); h->tasks.clear(); h->waves.clear();
-    h->tasks.reserve(n_task);
-    h->plots.reserve(n_task * 2);
-    std::vector<int8_t> has_lower(n_seq, -1);
-    auto seq_has_lower = [&](int32_t s) -> bool {
-        if (has_lower[s] < 0) {
-            const uint8_t* p = in->seq_bytes + in->seq_off[s];
-            const int64_t L = in->seq_off[s + 1] - in->seq_off[s];
-            int8_t f = 0;
-            int64_t i = 0;
-            // ASCII lower-case letters have bit 5 set, upper-case ones do not: skip 8 bytes at a time while no byte has it
-            for (; i + 8 <= L; i += 8) {
-                uint64_t w8; memcpy(&w8, p + i, 8);
-                if (w8 & 0x2020202020202020ull) {
-                    for (int j = 0; j < 8; ++j) if (p[i + j] >= 'a' && p[i + j] <= 'z') { f = 1; break; }
-                    if (f) break;
-                }
+    const bool trace = getenv("VAPOR_PLAN_TRACE") != nullptr;
+    auto tp0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[plan] %-10s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tp0).count());
+        tp0 = now;
+    };
+    // groups
+    std::vector<int64_t>& goff = h->group_off;
+    goff.clear();
+    if (n_sv > 0) goff.assign(in->sv_task_off, in->sv_task_off + n_sv + 1);
+    else { for (int64_t t = 0; t < n_task; t += 64) goff.push_back(t); goff.push_back(n_task); }
+    const int64_t n_groups = (int64_t)goff.size() - 1;
+
+    // phase A
+    int threads = h->plan_threads;
+    if (threads <= 0) {
+        const char* e = getenv("VAPOR_PLAN_THREADS");
+        threads = e ? atoi(e) : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 4u));
+    }
+    threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n_groups / 64 + 1));
+    if (!h->shards) h->shards = new std::vector<PlanShard>();
+    std::vector<PlanShard>& shards = *h->shards;
+    shards.resize((size_t)threads);
+    for (PlanShard& sh : shards) {
+        sh.ops.clear(); sh.plots.clear(); sh.tasks.clear(); sh.chunks.clear(); sh.items.clear(); sh.item_class.clear(); sh.jplots.clear();
+        sh.task_class.clear(); sh.k1chunks.clear(); sh.strips.clear();
+        sh.cells = sh.padded_cells = sh.bases = sh.probe_words = 0; sh.max_nb = 1; sh.rc = VAPOR_OK; sh.err.clear();
+    }
+    {   // contiguous group ranges of about equal task counts
+        int64_t g = 0;
+        for (int i = 0; i < threads; ++i) {
+            shards[(size_t)i].g0 = g;
+            const int64_t want = n_task * (i + 1) / threads;
+            while (g < n_groups && (i == threads - 1 || goff[(size_t)g + 1] <= want)) ++g;
+            shards[(size_t)i].g1 = g;
+        }
+        shards.back().g1 = n_groups;
+    }
+    std::vector<GroupSize> gsize((size_t)n_groups);
+    run_threads(threads, [&](int i) {
+        PlanShard& sh = shards[(size_t)i];
+        const int64_t nt = goff[(size_t)sh.g1] - goff[(size_t)sh.g0];
+        sh.tasks.reserve((size_t)nt); sh.plots.reserve((size_t)nt * 2); sh.ops.reserve((size_t)nt + (size_t)(sh.g1 - sh.g0) * 4);
+        plan_shard(h, in, goff, sh, gsize);
+    });
+    for (const PlanShard& sh : shards) if (sh.rc != VAPOR_OK) { h->err = sh.err; return sh.rc; }
+    lap("phase A");
+
+    // phase B: waves (cut at group boundaries by the memory budget: an eighth of the device memory free at open(),
+    // at most 16 GB, unless the caller set it) and the bases of every group
+    const int64_t budget_bytes = std::max<int64_t>(h->hit_budget > 0 ? h->hit_budget : h->default_hit_budget, (int64_t)1 << 19);
+    h->waves.clear();
+    std::vector<GroupBase> gbase((size_t)n_groups);
+    std::vector<int32_t> gwave((size_t)n_groups);
+    int64_t n_ops = 0, n_plots = 0, n_chunks = 0, n_jplots = 0, n_k1 = 0, n_strips = 0;
+    {
+        Wave cur{};
+        for (int64_t g = 0; g < n_groups; ++g) {
+            const GroupSize& gs = gsize[(size_t)g];
+            if (cur.bytes() >= budget_bytes && cur.task_end > cur.task_begin) {
+                h->waves.push_back(cur);
+                Wave nw{};
+                nw.task_begin = nw.task_end = cur.task_end; nw.plot_begin = nw.plot_end = cur.plot_end; nw.op_begin = nw.op_end = cur.op_end;
+                nw.chunk_begin = nw.chunk_end = cur.chunk_end;
+                cur = nw;
             }
-            for (; !f && i < L; ++i) if (p[i] >= 'a' && p[i] <= 'z') f = 1;
-            has_lower[s] = f;
+            GroupBase& gb = gbase[(size_t)g];
+            gb.op = n_ops; gb.plot = n_plots; gb.chunk = n_chunks; gb.jplot = n_jplots; gb.k1chunk = n_k1; gb.strip = n_strips;
+            gb.hash = cur.hash_elems; gb.code = cur.code_bytes; gb.table = cur.table_bytes; gb.hit = cur.hit_elems;
+            gwave[(size_t)g] = (int32_t)h->waves.size();
+            n_ops += gs.n_ops; n_plots += gs.n_plots; n_chunks += gs.n_chunks; n_jplots += gs.n_jplots; n_k1 += gs.n_k1chunks; n_strips += gs.n_strips;
+            cur.hash_elems += gs.hash_elems; cur.code_bytes += gs.code_bytes; cur.table_bytes += gs.table_bytes; cur.hit_elems += gs.hit_elems;
+            cur.task_end = goff[(size_t)g + 1]; cur.plot_end = n_plots; cur.op_end = n_ops; cur.chunk_end = n_chunks;
         }
-        return has_lower[s] != 0;
-    };
-
-    int64_t hash_off = 0, code_off = 0, cells = 0;
-    struct Key { int32_t seq, k, flags, op; };
-    std::vector<Key> local;                      // operand cache of the current SV
-    auto get_op = [&](int32_t seq, int k, int flags) -> int32_t {
-        for (auto& e : local) if (e.seq == seq && e.k == k && e.flags == flags) return e.op;
-        Operand o{};
-        o.seq_begin = in->seq_off[seq];
-        o.len = (int32_t)(in->seq_off[seq + 1] - in->seq_off[seq]);
-        o.k = k; o.flags = flags;
-        o.n = std::max(0, o.len - k + 1);
-        o.hash_off = hash_off; o.code_off = code_off;
-        hash_off += align4(o.n) + 8;
-        code_off += (o.len + 8 + 15) & ~15;          // 16-byte aligned code strings (8-byte stores in kernel 1)
-        h->ops.push_back(o);
-        int32_t id = (int32_t)h->ops.size() - 1;
-        local.push_back({seq, k, flags, id});
-        return id;
-    };
-    auto add_plot = [&](int32_t rop, int32_t sop, int32_t miss_bp) -> int32_t {
-        const Operand& r = h->ops[rop];
-        Operand& s = h->ops[sop];
-        // the reference slices ref_seq[miss_bp:] (Simple_function.pyx:185-186): a negative miss_bp, which
-        // cigar2alignstart_by_pos can return, counts from the end of the string as Python slicing does
-        const int32_t miss = miss_bp >= 0 ? miss_bp : std::max(0, s.len + miss_bp);
-        Plot p{};
-        p.read_op = rop; p.struct_op = sop; p.miss = miss;
-        p.n = r.n;
-        p.m = (miss <= s.len) ? std::max(0, s.len - miss - s.k + 1) : 0;
-        p.cap = (p.n > 0 && p.m > 0) ? (uint32_t)align4((int64_t)p.n + p.m + 32) : 0u;
-        p.hit_off = 0;
-        s.flags |= OPF_TABLE;
-        cells += (int64_t)p.n * p.m;
-        h->plots.push_back(p);
-        return (int32_t)h->plots.size() - 1;
-    };
-
-    int64_t sv_cursor = 0;
-    int64_t next_sv_end = n_sv > 0 ? in->sv_task_off[1] : n_task;
-    for (int64_t t = 0; t < n_task; ++t) {
-        while (n_sv > 0 && t >= next_sv_end && sv_cursor + 1 < n_sv) {
-            ++sv_cursor; next_sv_end = in->sv_task_off[sv_cursor + 1]; local.clear();
+        if (cur.task_end > cur.task_begin) h->waves.push_back(cur);
+    }
+    const size_t n_waves = h->waves.size();
+    // (wave, class) offsets of the join items and of the kernel-3 task lists; groups take their slots in order
+    h->jp.item_off.assign(n_waves * K2J_NCLASS + 1, 0);
+    h->class_off.assign(n_waves * K3_NCLASS + 1, 0);
+    for (int64_t g = 0; g < n_groups; ++g) {
+        const size_t wi = std::min<size_t>((size_t)gwave[(size_t)g], n_waves ? n_waves - 1 : 0);
+        if (!n_waves) break;
+        for (int c = 0; c < K2J_NCLASS; ++c) h->jp.item_off[wi * K2J_NCLASS + c + 1] += gsize[(size_t)g].n_items[c];
+        for (int c = 0; c < K3_NCLASS; ++c) h->class_off[wi * K3_NCLASS + c + 1] += gsize[(size_t)g].n_cls[c];
+    }
+    for (size_t i = 1; i < h->jp.item_off.size(); ++i) h->jp.item_off[i] += h->jp.item_off[i - 1];
+    for (size_t i = 1; i < h->class_off.size(); ++i) h->class_off[i] += h->class_off[i - 1];
+    {
+        std::vector<int64_t> icur(h->jp.item_off.begin(), h->jp.item_off.end()), ccur(h->class_off.begin(), h->class_off.end());
+        for (int64_t g = 0; g < n_groups && n_waves; ++g) {
+            const size_t wi = std::min<size_t>((size_t)gwave[(size_t)g], n_waves - 1);
+            GroupBase& gb = gbase[(size_t)g];
+            for (int c = 0; c < K2J_NCLASS; ++c) { gb.item[c] = icur[wi * K2J_NCLASS + c]; icur[wi * K2J_NCLASS + c] += gsize[(size_t)g].n_items[c]; }
+            for (int c = 0; c < K3_NCLASS; ++c) { gb.cls[c] = ccur[wi * K3_NCLASS + c]; ccur[wi * K3_NCLASS + c] += gsize[(size_t)g].n_cls[c]; }
         }
-        if (n_sv == 0 && (t & 63) == 0) local.clear();
-        const int32_t rs = in->task_read[t], fs = in->task_ref[t], as = in->task_alt[t];
-        const int32_t miss = in->task_miss[t];
-        const int k = in->task_k[t], mode = in->task_mode[t];
-        if (rs < 0 || rs >= n_seq || fs < 0 || fs >= n_seq || as < 0 || as >= n_seq) { h->err = "task sequence index out of range"; return VAPOR_E_ARG; }
-        if (k < 1 || k > K1_MAXK) { h->err = "window_size k must be 1..40"; return VAPOR_E_ARG; }
-        if (mode < 0 || mode > 3) { h->err = "unknown mode"; return VAPOR_E_ARG; }
-        Task tk{};
-        tk.mode = mode;
-        tk.len_ref = (int32_t)(in->seq_off[fs + 1] - in->seq_off[fs]);
-        tk.len_alt = (int32_t)(in->seq_off[as + 1] - in->seq_off[as]);
-        tk.read_op = get_op(rs, k, OPF_READ);
-        const bool abs_first = (mode == VAPOR_MODE_ABS || mode == VAPOR_MODE_ABS_AND_W10);
-        const int fl_ref = (abs_first && seq_has_lower(fs)) ? OPF_UPPER : 0;
-        const int fl_alt = (abs_first && seq_has_lower(as)) ? OPF_UPPER : 0;
-        tk.plot[0] = add_plot(tk.read_op, get_op(fs, k, fl_ref), miss);
-        tk.plot[1] = add_plot(tk.read_op, get_op(as, k, fl_alt), miss);
-        tk.plot[2] = tk.plot[3] = -1;
-        if (mode == VAPOR_MODE_ABS_AND_W10) {       // W10 does not upper-case (Simple_function.pyx:277-279)
-            tk.plot[2] = fl_ref ? add_plot(tk.read_op, get_op(fs, k, 0), miss) : tk.plot[0];
-            tk.plot[3] = fl_alt ? add_plot(tk.read_op, get_op(as, k, 0), miss) : tk.plot[1];
-        }
-        h->tasks.push_back(tk);
     }
 
-    // k1 chunks
-    h->chunk_prefix.assign(h->ops.size() + 1, 0);
-    int64_t bases = 0;
-    for (size_t i = 0; i < h->ops.size(); ++i) {
-        int chunks = std::max(1, (h->ops[i].len + K1_CHUNK - 1) / K1_CHUNK);
-        h->chunk_prefix[i + 1] = h->chunk_prefix[i] + chunks;
-        bases += h->ops[i].len;
-    }
-    // waves (plots were created in task order, so each wave is a contiguous plot range)
-    // hit slab of one wave: a quarter of the device memory free at open(), at most 24 GB, unless the caller set it
-    const int64_t budget_bytes = h->hit_budget > 0 ? h->hit_budget : h->default_hit_budget;
-    const int64_t budget_elems = std::max<int64_t>(budget_bytes / (int64_t)sizeof(uint2), 1 << 16);
+    lap("phase B");
+    // phase C
+    h->ops.resize((size_t)n_ops); h->plots.resize((size_t)n_plots); h->tasks.resize((size_t)n_task);
+    h->chunk_prefix.assign((size_t)n_ops + 1, 0); h->chunk_prefix[(size_t)n_ops] = (int32_t)n_k1;
+    h->strip_prefix.assign((size_t)n_plots + 1, 0);
+    h->class_ids.resize((size_t)n_task);
+    h->chunks.resize((size_t)n_chunks); h->jp.jplots.resize((size_t)n_jplots); h->jp.items.resize((size_t)h->jp.item_off.back());
+    lap("C alloc");
+    run_threads(threads, [&](int i) { place_shard(h, shards[(size_t)i], gsize, gbase); });
+    lap("phase C");
+
     h->plan_variant = h->tile_variant;
     h->plan_mode = h->k2_mode;
-    h->max_nb = 1; h->max_wave_hits = 0;
-    {
-        Wave w{0, 0, 0, 0, 0};
-        size_t pi = 0;
-        for (int64_t t = 0; t < n_task; ++t) {
-            int32_t last_plot = -1;
-            for (int i = 0; i < 4; ++i) last_plot = std::max(last_plot, h->tasks[t].plot[i]);
-            int64_t need = 0;
-            for (size_t q = pi; q <= (size_t)last_plot; ++q) need += h->plots[q].cap;
-            if (w.hit_elems + need > budget_elems && w.task_end > w.task_begin) {
-                h->waves.push_back(w);
-                w = Wave{t, t, (int64_t)pi, (int64_t)pi, 0};
-            }
-            for (size_t q = pi; q <= (size_t)last_plot; ++q) {
-                h->plots[q].hit_off = w.hit_elems;
-                w.hit_elems += h->plots[q].cap;
-                h->max_nb = std::max(h->max_nb, h->plots[q].n + h->plots[q].m - 1);
-            }
-            pi = (size_t)last_plot + 1;
-            w.task_end = t + 1; w.plot_end = (int64_t)pi;
-            h->max_wave_hits = std::max(h->max_wave_hits, w.hit_elems);
-        }
-        if (w.task_end > w.task_begin) h->waves.push_back(w);
+    h->max_nb = 1; h->max_wave_hits = 0; h->hash_elems = 0; h->code_bytes = 0; h->table_bytes = 0;
+    int64_t cells = 0, bases = 0, padded = 0, probe = 0, table_total = 0;
+    for (const PlanShard& sh : shards) { h->max_nb = std::max(h->max_nb, sh.max_nb); cells += sh.cells; bases += sh.bases; padded += sh.padded_cells; probe += sh.probe_words; }
+    for (const Wave& w : h->waves) {
+        h->max_wave_hits = std::max(h->max_wave_hits, w.hit_elems);
+        h->hash_elems = std::max(h->hash_elems, w.hash_elems);
+        h->code_bytes = std::max(h->code_bytes, w.code_bytes);
+        h->table_bytes = std::max(h->table_bytes, w.table_bytes);
+        table_total += w.table_bytes;
     }
-    // kernel-2 plan: strips of the tile kernel, or tables + items of the join kernel
-    int64_t padded_cells = 0;
-    h->strip_prefix.assign(h->plots.size() + 1, 0);
-    h->chunks.clear(); h->jp = JoinPlan{}; h->table_bytes = 0;
-    if (h->plan_mode == 0) {
-        for (size_t i = 0; i < h->plots.size(); ++i)
-            h->strip_prefix[i + 1] = h->strip_prefix[i] + cut_strips(h->plots[i], k2_variant_rows(h->plan_variant), &padded_cells);
-    } else {
-        std::vector<int32_t> op_chunk0;
-        h->table_bytes = build_chunks(h->ops, h->chunks, op_chunk0);
-        build_join_items(h->plots, h->waves, h->chunks, op_chunk0, h->jp);
-    }
-    h->tm_padded_cells = padded_cells;
-    // kernel-3 classes per wave
-    h->class_ids.resize(n_task);
-    h->class_off.assign(h->waves.size() * K3_NCLASS + 1, 0);
-    {
-        std::vector<int64_t> count(h->waves.size() * K3_NCLASS, 0);
-        std::vector<uint8_t> cls(n_task);
-        for (size_t wi = 0; wi < h->waves.size(); ++wi)
-            for (int64_t t = h->waves[wi].task_begin; t < h->waves[wi].task_end; ++t) {
-                int nb = 1;
-                for (int i = 0; i < 4; ++i) if (h->tasks[t].plot[i] >= 0) {
-                    const Plot& p = h->plots[h->tasks[t].plot[i]];
-                    nb = std::max(nb, p.n + p.m - 1);
-                }
-                cls[t] = (uint8_t)k3_class_of(nb);
-                ++count[wi * K3_NCLASS + cls[t]];
-            }
-        for (size_t i = 0; i < count.size(); ++i) h->class_off[i + 1] = h->class_off[i] + count[i];
-        std::vector<int64_t> cur(h->class_off.begin(), h->class_off.end() - 1);
-        for (size_t wi = 0; wi < h->waves.size(); ++wi)
-            for (int64_t t = h->waves[wi].task_begin; t < h->waves[wi].task_end; ++t)
-                h->class_ids[cur[wi * K3_NCLASS + cls[t]]++] = (int32_t)t;
-        // longest tasks first inside every launch (cost ~ rows + columns of the task's plots): short tasks fill the tail
-        std::vector<int32_t> cost(n_task);
-        for (int64_t t = 0; t < n_task; ++t) {
-            int c = 0;
-            for (int i = 0; i < 4; ++i) if (h->tasks[t].plot[i] >= 0) { const Plot& p = h->plots[h->tasks[t].plot[i]]; c += p.n + p.m; }
-            cost[t] = c;
-        }
-        for (size_t g = 0; g + 1 < h->class_off.size(); ++g)
-            std::stable_sort(h->class_ids.begin() + h->class_off[g], h->class_ids.begin() + h->class_off[g + 1],
-                             [&](int32_t a, int32_t b) { return cost[a] > cost[b]; });
-    }
+    h->hash_elems += 16; h->code_bytes += 64;
+    h->tm_padded_cells = padded;
     h->n_task = n_task; h->n_sv = n_sv; h->n_seq = n_seq;
     h->seq_total = n_seq > 0 ? in->seq_off[n_seq] : 0;
-    h->hash_elems = hash_off + 16; h->code_bytes = code_off + 64;
     h->tm = vapor_timings_t{};
-    h->tm.cells = cells; h->tm.n_plots = (int64_t)h->plots.size(); h->tm.n_operands = (int64_t)h->ops.size();
-    h->tm.padded_cells = h->tm_padded_cells;
-    h->tm.n_strips = h->plan_mode == 0 ? h->strip_prefix.back() : (int64_t)h->jp.items.size();
-    h->tm.n_waves = (int64_t)h->waves.size(); h->tm.bases = bases;
+    h->tm.cells = cells; h->tm.n_plots = n_plots; h->tm.n_operands = n_ops;
+    h->tm.padded_cells = padded;
+    h->tm.n_strips = h->plan_mode == 0 ? n_strips : (int64_t)h->jp.items.size();
+    h->tm.n_waves = (int64_t)n_waves; h->tm.bases = bases;
     h->tm.k2_mode = h->plan_mode;
-    h->tm.table_bytes = h->table_bytes;
-    { int64_t pw = 0; for (const Plot& p : h->plots) if (p.n > 0 && p.m > 0) pw += p.n; h->tm.probe_words = pw; }
+    h->tm.table_bytes = table_total;
+    h->tm.probe_words = probe;
     return VAPOR_OK;
 }
 
@@ -619,6 +825,17 @@ void launch_k3_class(Handle* h, K3Params kp, int c, int max_nb) {
     }
 }
 
+// kernel 1 over the operands of one wave; returns the launches made (0 or 1)
+int launch_k1_wave(Handle* h, const Wave& w) {
+    const int n_ops = (int)(w.op_end - w.op_begin);
+    if (n_ops <= 0) return 0;
+    const int base = h->chunk_prefix[w.op_begin], n_chunks = h->chunk_prefix[w.op_end] - base;
+    k1_pack_kmers<<<n_chunks, K1_THREADS, 0, h->stream>>>(
+        h->d_seq.p, h->d_ops.p + w.op_begin, h->d_chunk_prefix.p + w.op_begin, base, n_ops, h->d_hash.p, h->d_code.p,
+        h->d_op_status.p + w.op_begin);
+    return 1;
+}
+
 __global__ void k_sum_counts(const uint32_t* __restrict__ cnt, long long n, unsigned long long* out) {
     unsigned long long s = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += cnt[i];
@@ -703,6 +920,7 @@ int redo_wave(Handle* h, size_t wi, int64_t* launches) {
     CKR(cudaMemcpyAsync(d_out.p, out_flat.data(), out_flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CKR(cudaMemsetAsync(d_recnt.p, 0, re_plots.size() * sizeof(uint32_t), h->stream));
     CKR(cudaMemsetAsync(d_reflag.p, 0, 4 * sizeof(uint32_t), h->stream));
+    if (h->waves.size() > 1) *launches += launch_k1_wave(h, w);      // later waves reused the word / code buffers
     CKR(cudaMemsetAsync(h->d_queue.p, 0, 4 * sizeof(unsigned long long), h->stream));
     int sp = span_begin(h, CAT_TILE);
     if (re_prefix.back() > 0) {
@@ -744,28 +962,26 @@ int run_impl(Handle* h) {
     h->spans.clear(); h->ev_used = 0;
     CK(cudaEventRecord(h->ev_run0, h->stream));
 
-    // ---- kernel 1 (+ 1b: tables of the structure-side operands) ---------------------------------
-    int sp = span_begin(h, CAT_PACK);
     CK(cudaMemsetAsync(h->d_op_status.p, 0, (h->ops.size() + 1) * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(h->d_cnt.p, 0, (h->plots.size() + 1) * sizeof(uint32_t), h->stream));
     CK(cudaMemsetAsync(h->d_ovf_flags.p, 0, (h->waves.size() + 1) * sizeof(uint32_t), h->stream));
     CK(cudaMemsetAsync(h->d_stats.p, 0, 4 * sizeof(unsigned long long), h->stream));
-    if (!h->ops.empty()) {
-        k1_pack_kmers<<<h->chunk_prefix.back(), K1_THREADS, 0, h->stream>>>(
-            h->d_seq.p, h->d_ops.p, h->d_chunk_prefix.p, (int)h->ops.size(), h->d_hash.p, h->d_code.p, h->d_op_status.p);
-        ++launches;
-    }
-    span_end(h, sp);
-    if (h->plan_mode == 1 && !h->chunks.empty()) {
-        sp = span_begin(h, CAT_TABLE);
-        k1b_build_tables<<<(unsigned)h->chunks.size(), K1B_THREADS, 0, h->stream>>>(h->d_chunks.p, h->d_ops.p, h->d_hash.p, h->d_table.p);
-        ++launches;
-        span_end(h, sp);
-    }
-    CK(cudaGetLastError());
 
+    int sp;
     for (size_t wi = 0; wi < h->waves.size(); ++wi) {
         const Wave& w = h->waves[wi];
+        // ---- kernel 1 (+ 1b: tables of the structure-side operands) of this wave's operands ---------------
+        sp = span_begin(h, CAT_PACK);
+        launches += launch_k1_wave(h, w);
+        span_end(h, sp);
+        if (h->plan_mode == 1 && w.chunk_end > w.chunk_begin) {
+            sp = span_begin(h, CAT_TABLE);
+            k1b_build_tables<<<(unsigned)(w.chunk_end - w.chunk_begin), K1B_THREADS, 0, h->stream>>>(
+                h->d_chunks.p + w.chunk_begin, h->d_ops.p, h->d_hash.p, h->d_table.p);
+            ++launches;
+            span_end(h, sp);
+        }
+        CK(cudaGetLastError());
         // ---- kernel 2 ---------------------------------------------------------------------
         sp = span_begin(h, CAT_TILE);
         if (h->plan_mode == 0) {
@@ -1034,7 +1250,7 @@ int vapor_gpu_open(int device, void** handle) {
     {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > 0)
-            h->default_hit_budget = std::max<int64_t>((int64_t)1 << 30, std::min<int64_t>((int64_t)24 << 30, (int64_t)(free_b / 4)));
+            h->default_hit_budget = std::max<int64_t>((int64_t)1 << 30, std::min<int64_t>((int64_t)16 << 30, (int64_t)(free_b / 8)));
     }
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_open_error = cudaGetErrorString(e); delete h; return VAPOR_E_CUDA; }
@@ -1218,8 +1434,10 @@ int vapor_gpu_selfplot_qc(void* handle, const uint8_t* seq_bytes, const int64_t*
     std::vector<TabChunk> chunks; JoinPlan jp; int64_t table_bytes = 0;
     if (mode == 1) {
         std::vector<int32_t> op_chunk0;
-        table_bytes = build_chunks(ops, chunks, op_chunk0);
-        std::vector<Wave> one{Wave{0, 0, 0, (int64_t)ns, 0}};
+        Wave w1{};
+        w1.plot_end = (int64_t)ns; w1.op_end = (int64_t)ns;
+        std::vector<Wave> one{w1};
+        table_bytes = build_chunks(ops, one, chunks, op_chunk0);
         build_join_items(plots, one, chunks, op_chunk0, jp);
     }
     CK(h->d_seq.ensure((size_t)total + 64)); CK(h->d_ops.ensure(ns + 1)); CK(h->d_plots.ensure(ns + 1));
@@ -1250,7 +1468,7 @@ int vapor_gpu_selfplot_qc(void* handle, const uint8_t* seq_bytes, const int64_t*
     CK(cudaMemsetAsync(h->d_ovf_flags.p, 0, 4 * sizeof(uint32_t), h->stream));
     CK(cudaMemsetAsync(h->d_stats.p, 0, 4 * sizeof(unsigned long long), h->stream));
     k1_pack_kmers<<<chunk_prefix.back(), K1_THREADS, 0, h->stream>>>(
-        h->d_seq.p, h->d_ops.p, h->d_chunk_prefix.p, (int)ns, h->d_hash.p, h->d_code.p, h->d_op_status.p);
+        h->d_seq.p, h->d_ops.p, h->d_chunk_prefix.p, 0, (int)ns, h->d_hash.p, h->d_code.p, h->d_op_status.p);
     CK(cudaGetLastError());
     if (mode == 0) {
         if (strip_prefix.back() > 0) {
@@ -1323,6 +1541,33 @@ int vapor_gpu_host_alloc(void** p, int64_t bytes) {
 int vapor_gpu_host_free(void* p) {
     if (!p) return VAPOR_OK;
     return cudaFreeHost(p) == cudaSuccess ? VAPOR_OK : VAPOR_E_CUDA;
+}
+
+int vapor_host_plan(const vapor_batch_t* in, int k2_mode, int threads, int64_t wave_budget_bytes, double* ms, uint64_t* digest, int64_t* counts) {
+    Handle h;                                    // no device is touched: planning is host work
+    h.k2_mode = k2_mode ? 1 : 0; h.plan_threads = threads; h.hit_budget = wave_budget_bytes;
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = plan_batch(&h, in);
+    if (ms) *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (rc) { g_open_error = h.err; return rc; }
+    if (digest) {                                // FNV-1a over everything the kernels will read
+        uint64_t d = 1469598103934665603ull;
+        auto mixin = [&](const void* p, size_t n) { const uint8_t* b = static_cast<const uint8_t*>(p); for (size_t i = 0; i < n; ++i) { d ^= b[i]; d *= 1099511628211ull; } };
+        mixin(h.ops.data(), h.ops.size() * sizeof(Operand)); mixin(h.plots.data(), h.plots.size() * sizeof(Plot));
+        mixin(h.tasks.data(), h.tasks.size() * sizeof(Task)); mixin(h.chunk_prefix.data(), h.chunk_prefix.size() * sizeof(int32_t));
+        mixin(h.class_ids.data(), h.class_ids.size() * sizeof(int32_t)); mixin(h.class_off.data(), h.class_off.size() * sizeof(int64_t));
+        mixin(h.chunks.data(), h.chunks.size() * sizeof(TabChunk)); mixin(h.jp.items.data(), h.jp.items.size() * sizeof(JoinItem));
+        mixin(h.jp.jplots.data(), h.jp.jplots.size() * sizeof(int32_t)); mixin(h.jp.item_off.data(), h.jp.item_off.size() * sizeof(int64_t));
+        mixin(h.strip_prefix.data(), h.strip_prefix.size() * sizeof(int64_t));
+        for (const Wave& w : h.waves) mixin(&w, sizeof(Wave));
+        *digest = d;
+    }
+    if (counts) {
+        counts[0] = (int64_t)h.ops.size(); counts[1] = (int64_t)h.plots.size(); counts[2] = (int64_t)h.tasks.size();
+        counts[3] = (int64_t)h.waves.size(); counts[4] = (int64_t)h.chunks.size(); counts[5] = (int64_t)h.jp.items.size();
+        counts[6] = h.tm.cells; counts[7] = h.max_wave_hits;
+    }
+    return VAPOR_OK;
 }
 
 int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s) {

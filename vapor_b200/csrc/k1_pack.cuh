@@ -187,8 +187,8 @@ __device__ __forceinline__ bool k1_run(const uint8_t* s_code, const Operand& op,
 
 __global__ void __launch_bounds__(K1_THREADS, K1_MINB)
 k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
-              const int32_t* __restrict__ chunk_prefix,   // [n_ops+1] cumulative chunk counts
-              int n_ops, uint32_t* __restrict__ hash, uint8_t* __restrict__ code,
+              const int32_t* __restrict__ chunk_prefix,   // [n_ops+1] cumulative chunk counts, offset by chunk_base
+              int chunk_base, int n_ops, uint32_t* __restrict__ hash, uint8_t* __restrict__ code,
               int32_t* __restrict__ op_status)
 {
     __shared__ uint8_t s_lut[256];                               // the alphabet table, out of the constant cache:
@@ -200,10 +200,10 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
     const int bid = blockIdx.x;
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
-        if (chunk_prefix[mid] <= bid) lo = mid; else hi = mid;
+        if (chunk_prefix[mid] - chunk_base <= bid) lo = mid; else hi = mid;
     }
     const Operand op = ops[lo];
-    const int chunk = bid - chunk_prefix[lo];
+    const int chunk = bid - (chunk_prefix[lo] - chunk_base);
     const int base0 = chunk * K1_CHUNK;
     const int k = op.k;
     const int nload = min(K1_CHUNK + k - 1, op.len - base0);     // bases this CTA needs

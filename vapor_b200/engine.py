@@ -349,9 +349,11 @@ class Engine:
 
 class Pipeline:
     """Double-buffered scoring of a stream of batches on one GPU: ``depth`` handles (``vapor_gpu_open`` each, own
-    stream and device buffers), one worker thread per handle.  While one handle's kernels run, the next batch is
-    planned on the host and copied in on another handle, so host planning + H2D hide under the kernels
-    (the C-ABI call releases the GIL).  Results come back in submission order.
+    stream and device buffers), one worker thread per handle.  Every batch goes through the three public steps
+    ``vapor_gpu_upload`` (host planning + H2D), ``vapor_gpu_run`` (kernels), ``vapor_gpu_fetch`` (D2H); one lock per
+    step keeps the handles out of each other's way, so while one handle's kernels run the next batch is planned and
+    copied in on the other: the steps form a pipeline whose beat is the slowest step instead of their sum
+    (the C-ABI calls release the GIL).  Results come back in submission order.
 
         with Pipeline(device=0, depth=2) as pipe:
             for res in pipe.map(batches): ...
@@ -374,7 +376,6 @@ class Pipeline:
         """Score every batch; ``results[i]`` (optional) is a caller-provided (e.g. pinned) Results to fill.
         ``after(results_i)`` (optional) runs in the worker thread right after batch i was scored -- e.g. the scatter
         of a shard's results into shared input-order arrays -- while the other handle keeps the GPU busy."""
-        import queue
         import threading
         batches = list(batches)
         n = len(batches)
@@ -382,6 +383,7 @@ class Pipeline:
         errs: List[BaseException] = []
         nxt = [0]
         lock = threading.Lock()
+        copy_in, kernels, copy_out = threading.Lock(), threading.Lock(), threading.Lock()
 
         def work(eng):
             while True:
@@ -392,7 +394,12 @@ class Pipeline:
                     return
                 try:
                     into = results[i] if results is not None and results[i] is not None else _alloc_results(batches[i].n_task, batches[i].n_sv)
-                    out[i] = eng.score_into(batches[i], into)
+                    with copy_in:
+                        eng.upload(batches[i])
+                    with kernels:
+                        eng.run()
+                    with copy_out:
+                        out[i] = eng.fetch(into)
                     if after is not None:
                         after(out[i])
                 except BaseException as e:          # noqa: BLE001
@@ -406,6 +413,19 @@ class Pipeline:
         if errs:
             raise errs[0]
         return out
+
+
+def host_plan(batch: PackedBatch, k2_mode: int = 1, threads: int = 0, wave_budget_bytes: int = 0) -> dict:
+    """``vapor_host_plan``: plan a batch on the host only (no GPU needed): wall ms, plan digest, counts."""
+    lib = N.load()
+    b = batch.c_struct()
+    ms, dg = C.c_double(0), C.c_uint64(0)
+    cnt = (C.c_int64 * 8)()
+    rc = lib.vapor_host_plan(C.byref(b), int(k2_mode), int(threads), int(wave_budget_bytes), C.byref(ms), C.byref(dg), cnt)
+    if rc != 0:
+        raise N.VaporNativeError(f"vapor_host_plan failed ({rc}): {lib.vapor_gpu_last_error(None).decode()}")
+    names = ("operands", "plots", "tasks", "waves", "table_chunks", "join_items", "cells", "max_wave_hits")
+    return {"ms": ms.value, "digest": dg.value, **{n: int(v) for n, v in zip(names, cnt)}}
 
 
 def hit_mix(x, y) -> np.ndarray:
