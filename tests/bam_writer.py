@@ -47,8 +47,14 @@ def write_bam(path, refs, records, block_records=40, with_bai=True):
         sq = bytearray((len(seq) + 1) // 2)
         for j, c in enumerate(seq):
             sq[j // 2] |= _SEQ_ENC.get(c, 15) << (4 if j % 2 == 0 else 0)
-        body = struct.pack("<iiBBHHHiiii", tid, pos0, len(qname) + 1, 60, b, len(cig), 0, len(seq), -1, -1, 0)
-        body += qname.encode() + b"\x00" + b"".join(struct.pack("<I", (n << 4) | op) for n, op in cig) + bytes(sq) + b"\xff" * len(seq)
+        aux = b""
+        cig_field = cig
+        if len(cig) > 65535:              # SAM spec 4.2.2: <l_seq>S<ref_len>N in the field, the real CIGAR in CG:B,I
+            cig_field = [(len(seq), 4), (span, 3)]
+            aux = b"CGBI" + struct.pack("<I", len(cig)) + b"".join(struct.pack("<I", (n << 4) | op) for n, op in cig)
+        body = struct.pack("<iiBBHHHiiii", tid, pos0, len(qname) + 1, 60, b, len(cig_field), 0, len(seq), -1, -1, 0)
+        body += (qname.encode() + b"\x00" + b"".join(struct.pack("<I", (n << 4) | op) for n, op in cig_field) + bytes(sq) +
+                 b"\xff" * len(seq) + b"NMC\x03" + aux)
         rec = struct.pack("<i", len(body)) + body
         if len(cur) and (i % block_records == 0 or len(cur) + len(rec) > 60000):
             blocks.append(cur); cur = b""

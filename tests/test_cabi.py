@@ -8,8 +8,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_functions():
-    src = open(os.path.join(ROOT, "include", "vapor_b200.h")).read()
+def _declared_functions(header="vapor_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(vapor_[a-z0-9_]+)\s*\(", src)))
 
@@ -24,6 +24,13 @@ def test_header_symbols_exported():
         assert hasattr(lib, name), f"{name} declared in include/vapor_b200.h but not exported"
     assert sorted(_native.EXPORTS) == declared
     assert lib.vapor_b200_abi_version() == 2
+    # the native region extraction (include/vapor_hostio.h) lives in the same library
+    from vapor_b200 import _hostio
+    io_declared = _declared_functions("vapor_hostio.h")
+    assert len(io_declared) >= 10
+    for name in io_declared:
+        assert hasattr(lib, name), f"{name} declared in include/vapor_hostio.h but not exported"
+    assert sorted(_hostio.EXPORTS) == io_declared
 
 
 def test_hit_mix_host_callable_matches_numpy():

@@ -324,6 +324,8 @@ def chop_pacbio_read_by_pos(bam_in_new, chrom, start, end, flank_length):
     """Reads of ``samtools view bam chrom:start-end`` cut to the window: ``[[read, miss_bp, qname], ...]``
     (Simple_function.pyx:339-354).  Keeps alignments starting at or before ``start`` whose missed bases do
     not exceed half the flank and that run past the window end."""
+    if seqio.native_enabled():                  # csrc/hostio.cpp: the same rules in native code
+        return seqio.chop_reads([bam_in_new], chrom, start, end, flank_length, max_reads=0)
     out = []
     for rec in seqio.view(bam_in_new, chrom, start, end):
         if rec.pos < start + 1:
@@ -368,6 +370,8 @@ def bam_in_decide(bam_in, bps):
 
 def simple_del_chop_pacbio_read_simple_short(bam_in, sv_info, flank_length):
     """Reads around the left breakpoint: window ``[s - f, s + f]`` (Simple_function.pyx:1378-1390)."""
+    if seqio.native_enabled():                  # every file, the window cut and the 20-read cap in one native call
+        return seqio.chop_reads(bam_in_decide(bam_in, sv_info), sv_info[0], int(sv_info[1]) - flank_length, int(sv_info[1]) + flank_length, flank_length)
     x = []
     for b in bam_in_decide(bam_in, sv_info):
         x += chop_pacbio_read_by_pos(b, sv_info[0], int(sv_info[1]) - flank_length, int(sv_info[1]) + flank_length, flank_length)
@@ -376,6 +380,8 @@ def simple_del_chop_pacbio_read_simple_short(bam_in, sv_info, flank_length):
 
 def simple_chop_pacbio_read_simple_short(bam_in, sv_info, flank_length):
     """Reads across the whole event: window ``[s - f, last + f]`` (Simple_function.pyx:1392-1401)."""
+    if seqio.native_enabled():
+        return seqio.chop_reads(bam_in_decide(bam_in, sv_info), sv_info[0], int(sv_info[1]) - flank_length, int(sv_info[-1]) + flank_length, flank_length)
     x = []
     for b in bam_in_decide(bam_in, sv_info):
         x += chop_pacbio_read_by_pos(b, sv_info[0], int(sv_info[1]) - flank_length, int(sv_info[-1]) + flank_length, flank_length)

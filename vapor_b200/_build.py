@@ -8,9 +8,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libvapor_b200.so")
-SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "k1_pack.cuh", "k2_tile.cuh", "k3_score.cuh", "k4_genotype.cuh",
-           os.path.join("..", "..", "include", "vapor_b200.h")]
+SOURCES = ["api.cu", "hostio.cpp"]
+HEADERS = ["common.cuh", "k1_pack.cuh", "k2_tile.cuh", "k2_join.cuh", "k3_score.cuh", "k4_genotype.cuh",
+           os.path.join("..", "..", "include", "vapor_b200.h"), os.path.join("..", "..", "include", "vapor_hostio.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
@@ -36,7 +36,7 @@ def build_native(force: bool = False, verbose: bool = False, out: str = "", extr
         return LIB
     extra = os.environ.get("VAPOR_NVCC_EXTRA", "").split() + list(extra_flags)     # experiments only, e.g. -DK2_MINB=6
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", out or LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+          ["-o", out or LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lz"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -238,6 +238,34 @@ class _BgzfReader:
         return b"".join(out)
 
 
+_AUX_SIZE = {"A": 1, "c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4}
+
+
+def _cg_tag(rec: bytes, p: int):
+    """The uint32 array of the CG:B,I auxiliary field of a BAM record (aux fields start at ``p``), or None."""
+    n = len(rec)
+    while p + 3 <= n:
+        tag, ty = rec[p:p + 2], chr(rec[p + 2])
+        p += 3
+        if ty in _AUX_SIZE:
+            p += _AUX_SIZE[ty]
+        elif ty in "ZH":
+            while p < n and rec[p]:
+                p += 1
+            p += 1
+        elif ty == "B":
+            if p + 5 > n:
+                return None
+            sub, cnt = chr(rec[p]), struct.unpack_from("<I", rec, p + 1)[0]
+            es = 1 if sub in "cC" else (2 if sub in "sS" else 4)
+            if tag == b"CG" and sub == "I" and p + 5 + 4 * cnt <= n:
+                return struct.unpack_from(f"<{cnt}I", rec, p + 5)
+            p += 5 + es * cnt
+        else:
+            return None
+    return None
+
+
 def _reg2bins(beg: int, end: int) -> List[int]:
     end -= 1
     bins = [0]
@@ -315,6 +343,17 @@ class _Bam:
                     span += ln
             nb = (l_seq + 1) // 2
             sq = rec[p:p + nb]
+            if n_cig == 2 and (cig[0] & 15) == 4 and (cig[0] >> 4) == l_seq and (cig[1] & 15) == 3:
+                # more than 65535 operations: the field holds <l_seq>S<ref_len>N, the real CIGAR sits in the CG:B,I tag
+                # (samtools view, which the reference shells out to, prints the real one)
+                real = _cg_tag(rec, p + nb + l_seq)
+                if real is not None:
+                    span, parts = 0, []
+                    for c in real:
+                        ln, op = c >> 4, c & 15
+                        parts.append(f"{ln}{_CIG_OPS[op]}")
+                        if op in (0, 2, 3, 7, 8):
+                            span += ln
             seq = "".join(_SEQ_DEC[b >> 4] + _SEQ_DEC[b & 15] for b in sq)[:l_seq]
             yield tid, pos + 1, pos + max(span, 1), AlnRecord(qname, pos + 1, "".join(parts) or "*", seq or "*")
 
@@ -383,6 +422,73 @@ def alignments(path: str) -> AlignmentFile:
     return _aln_cache[key]
 
 
+# ----------------------------------------------------------------------------------------------------
+# native route (csrc/hostio.cpp through _hostio): the default.  VAPOR_HOSTIO=python keeps everything above in charge
+# (the pure-Python readers are what the native ones are tested against).
+# ----------------------------------------------------------------------------------------------------
+def native_enabled() -> bool:
+    return os.environ.get("VAPOR_HOSTIO", "native") != "python" and not use_samtools()
+
+
+_native_fa: Dict[str, object] = {}
+_native_aln: Dict[str, object] = {}
+_region_cache: Dict[tuple, str] = {}          # prefetched samtools-faidx answers
+_reads_cache: Dict[tuple, list] = {}           # prefetched chop + minimize answers
+
+
+def native_fasta(path: str):
+    from . import _hostio
+    f = _native_fa.get(path)
+    if f is None:
+        f = _native_fa[path] = _hostio.FastaIndex(path)
+    return f
+
+
+def native_aln(path: str):
+    from . import _hostio
+    a = _native_aln.get(path)
+    if a is None:
+        a = _native_aln[path] = _hostio.AlnFile(path)
+    return a
+
+
+def chop_reads(files, chrom: str, start: int, end: int, flank: int, max_reads: int = 20) -> list:
+    """``[[read, miss_bp, qname], ...]`` of one window over ``files`` in order: chop_pacbio_read_by_pos per file
+    (Simple_function.pyx:339-354), concatenated, then minimize_pacbio_read_list when ``max_reads`` > 0 (:1091-1102).
+    Native route only (callers check ``native_enabled()``)."""
+    key = (tuple(files), chrom, int(start), int(end), int(flank), int(max_reads))
+    hit = _reads_cache.get(key)
+    if hit is not None:
+        return [list(x) for x in hit]
+    from . import _hostio
+    out, _ = _hostio.chop_many([native_aln(f) for f in files], [(chrom, int(start), int(end), int(flank))], max_reads=max_reads, threads=1)
+    return out[0]
+
+
+def prefetch(ref: str, regions, files, windows, max_reads: int = 20, threads: int = 0) -> None:
+    """Answer many queries ahead of the drivers in two native calls on several host threads: ``regions`` =
+    ``(chrom, start, end)`` of ``samtools faidx ref``, ``windows`` = ``(chrom, start, end, flank)`` of chop + minimize
+    over ``files``.  The answers wait in caches that ``faidx`` / ``chop_reads`` consult first; ``clear_prefetch`` drops them."""
+    if not native_enabled():
+        return
+    from . import _hostio
+    regions = [r for r in dict.fromkeys((c, int(a), int(b)) for c, a, b in regions) if (ref,) + r not in _region_cache]
+    if regions:
+        for r, s in zip(regions, native_fasta(ref).fetch_many(regions, threads)):
+            _region_cache[(ref,) + r] = s
+    files = tuple(files)
+    windows = [w for w in dict.fromkeys((c, int(a), int(b), int(f)) for c, a, b, f in windows) if (files,) + w + (max_reads,) not in _reads_cache]
+    if windows and files:
+        lists, _ = _hostio.chop_many([native_aln(f) for f in files], windows, max_reads=max_reads, threads=threads)
+        for w, l in zip(windows, lists):
+            _reads_cache[(files,) + w + (max_reads,)] = l
+
+
+def clear_prefetch() -> None:
+    _region_cache.clear()
+    _reads_cache.clear()
+
+
 def faidx(ref: str, chrom: str, start: int, end: int) -> str:
     """The sequence ``ref_seq_readin`` assembles from ``samtools faidx ref chrom:start-end``
     (Simple_function.pyx:1206-1213): header dropped, lines joined."""
@@ -395,6 +501,9 @@ def faidx(ref: str, chrom: str, start: int, end: int) -> str:
                 break
             seq += f[0]
         return seq
+    if native_enabled():
+        hit = _region_cache.get((ref, chrom, int(start), int(end)))
+        return hit if hit is not None else native_fasta(ref).fetch(chrom, int(start), int(end))
     return fasta(ref).fetch(chrom, start, end)
 
 
