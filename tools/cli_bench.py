@@ -29,7 +29,10 @@ def main():
                                    coverage=args.coverage, read_len_mean=8000.0)
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
-    seqio.fasta(ds.ref_fa); seqio.alignments(ds.sam)            # parse + index once (cached for the run)
+    if seqio.native_enabled():                                  # parse + index once (cached for the run)
+        seqio.native_fasta(ds.ref_fa); seqio.native_aln(ds.sam)
+    else:
+        seqio.fasta(ds.ref_fa); seqio.alignments(ds.sam)
     t_load = time.perf_counter() - t0
     sessions = [SF.Session(0)] if args.gpus == 1 else args.gpus          # N > 1: one worker process per GPU
     if args.gpus == 1:
@@ -50,7 +53,7 @@ def main():
         stats = dict(sessions[0].stats)
         sessions[0].close()
     called = sum(1 for r in rows if len(r) > 4)
-    print(json.dumps({"n_sv": args.n_sv, "gpus": args.gpus, "rows": len(rows), "rows_with_scores": called,
+    print(json.dumps({"n_sv": args.n_sv, "gpus": args.gpus, "host_io": "native" if seqio.native_enabled() else "python", "rows": len(rows), "rows_with_scores": called,
                       "generate_s": round(t_gen, 2), "load_index_s": round(t_load, 2), "vapor_bed_s": round(t_run, 2),
                       "sv_per_s": round(len(rows) / t_run, 1), "reads_scored": stats["reads_scored"],
                       "reads_per_s": round(stats["reads_scored"] / t_run, 1) if stats["reads_scored"] else None, "session": stats}))

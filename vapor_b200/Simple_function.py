@@ -75,8 +75,13 @@ def reverse(seq):
 _COMP = {a: b for a, b in zip("ATGCNatgcn", "TACGNtacgn")}
 
 
+_COMP_TABLE = {c: (ord(_COMP[chr(c)]) if chr(c) in _COMP else None) for c in range(0x110000 if False else 256)}
+
+
 def complementary(seq):
     """Simple_function.pyx:471-478.  # quirk: characters outside ATGCN/atgcn are *dropped*, not kept."""
+    if seq.isascii():
+        return seq.translate(_COMP_TABLE)
     return "".join(_COMP[c] for c in seq if c in _COMP)
 
 
@@ -462,7 +467,7 @@ class Session:
         k-mer size evaluated in one ``vapor_gpu_selfplot_qc`` call."""
         n = len(reqs)
         out: List[Optional[list]] = [None] * n
-        seqs = ["".join(c for c in r.seq if c != "X") for r in reqs]
+        seqs = [r.seq.replace("X", "") for r in reqs]
         k = [10] * n
         live = []
         for i, s in enumerate(seqs):
@@ -1178,6 +1183,60 @@ def co_cannot_classify(num_reads_cff, plt_li, bam_in, ref, sv_info, out_figure_n
                         if len(reads) > 0:
                             out += yield from _score(ref_seq_a, alt_seq, reads, k, MODE_W10, None)
     return out
+
+
+# ---- bulk prefetch of the drivers' primary region / read queries ---------------------------------------------
+def primary_queries(name, args):
+    """What a driver coroutine will ask first, known from its arguments alone: ``(ref, bam_in, [(chrom, start, end)
+    faidx regions], [(chrom, start, end, flank) read windows])``.  Fallback paths (junction windows when too few reads
+    span the event) are left to the per-call route."""
+    regions, windows = [], []
+    if name in ("co_simple_del", "co_simple_inv", "co_simple_tandup"):
+        _cff, _plt, bam_in, ref, sv_info, _fig = args
+        c, s, e = sv_info[0], int(sv_info[1]), int(sv_info[2])
+        f = flank_length_calculate(sv_info)
+        if e - s < default_max_sv_test:
+            regions.append((c, s - f, e + f))
+            if name == "co_simple_del":
+                windows.append((c, s - f, s + f, f))
+            elif name == "co_simple_inv":
+                windows.append((c, s - f, e + f, f))
+            else:
+                windows.append((c, s - f, s + 2 * (e - s) + f, f))
+        elif name == "co_simple_del":
+            regions += [(c, s - f, s + f), (c, s - f, s), (c, e, e + f)]
+            windows.append((c, s - f, s + f, f))
+        return ref, bam_in, regions, windows
+    if name == "co_simple_ins":
+        _cff, _plt, bam_in, ref, ins_pos, ins_seq, _fig, _pol = args
+        f = default_flank_length if len(ins_seq) > default_flank_length else len(ins_seq)
+        c, pos = "_".join(ins_pos.split("_")[:-1]), int(ins_pos.split("_")[-1])
+        windows.append((c, pos - f, pos + len(ins_seq) + f, f))
+        regions += [(c, pos - f, pos + f + len(ins_seq)) if len(ins_seq) < 5000 else (c, pos - f, pos + f), (c, pos - f, pos), (c, pos, pos + f)]
+        return ref, bam_in, regions, windows
+    return None
+
+
+def prefetch_events(specs, threads=0):
+    """Answer the primary queries of many events in two native calls per (reference, read files) pair
+    (seqio.prefetch: several host threads) before their coroutines run; the coroutines then find them in the cache."""
+    if not seqio.native_enabled():
+        return 0
+    groups: Dict[tuple, list] = {}
+    for name, args in specs:
+        q = primary_queries(name, args)
+        if q is None:
+            continue
+        ref, bam_in, regions, windows = q
+        g = groups.setdefault((ref, bam_in), [[], []])
+        g[0] += regions
+        g[1] += windows
+    n = 0
+    for (ref, bam_in), (regions, windows) in groups.items():
+        files = bam_in_decide(bam_in, None)
+        seqio.prefetch(ref, regions, files, windows, threads=threads)
+        n += len(regions) + len(windows)
+    return n
 
 
 # ---- drop-in wrappers: the reference signatures, one event at a time ----------------------------------

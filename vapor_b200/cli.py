@@ -15,7 +15,7 @@ import threading
 from typing import Callable, List, Sequence
 
 from . import Simple_function as SF
-from . import prep
+from . import prep, seqio
 
 
 # ---- input parsers: host-only restatements of vapor_vali/vapor:22-50, 84-202, 255-268 -------------------
@@ -198,6 +198,9 @@ def _shard_worker(job):
         SF.set_session(None)
 
 
+EVENT_CHUNK = 4000          # events whose drivers run (and whose reads are prefetched) together
+
+
 def score_events(events: Sequence[Event], sessions) -> List[list]:
     """Run every event's driver and summarise.  ``sessions`` is a list of open Sessions (events are sharded
     round-robin over them, one thread each) or an int N > 1: N worker *processes*, one per GPU -- the host side of
@@ -227,10 +230,17 @@ def score_events(events: Sequence[Event], sessions) -> List[list]:
         def work(si):
             try:
                 SF.set_session(sessions[si], thread_only=True)   # figure hooks use the calling thread's session
-                idx = live[si::n_s]
-                res = sessions[si].run_events([events[i].make() for i in idx])
-                for i, r in zip(idx, res):
-                    score_lists[i] = r if r is not None else []
+                mine = live[si::n_s]
+                # chunks bound the memory of the prefetched reads (20 reads x a few kb per event)
+                for c0 in range(0, len(mine), EVENT_CHUNK):
+                    idx = mine[c0:c0 + EVENT_CHUNK]
+                    if n_s == 1:
+                        SF.prefetch_events([events[i].spec for i in idx])
+                    res = sessions[si].run_events([events[i].make() for i in idx])
+                    for i, r in zip(idx, res):
+                        score_lists[i] = r if r is not None else []
+                    if n_s == 1:
+                        seqio.clear_prefetch()
             except BaseException as e:                  # noqa: BLE001
                 errs.append(e)
         if n_s == 1:
