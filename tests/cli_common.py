@@ -83,17 +83,33 @@ def run_bed_case(tmp_path, session, case=None):
     compare_bed_tables(out, os.path.join(case, "svs.bed.vapor.golden"))
 
 
-def run_vcf_case(tmp_path, session):
+CASE_COMPLEX = os.path.join(HERE, "golden", "cli_case_complex")
+
+
+def run_vcf_case(tmp_path, session, case=None, first_records=0):
+    """``first_records`` > 0: only the first records of the VCF (and of the golden table, which keeps the VCF's order)."""
+    case = case or CASE
     vcf = os.path.join(str(tmp_path), "svs_nohdr.vcf")
-    shutil.copy(os.path.join(CASE, "svs_nohdr.vcf"), vcf)
+    gold = os.path.join(case, "svs_nohdr.vcf.vapor.golden")
+    if first_records:
+        with open(os.path.join(case, "svs_nohdr.vcf")) as f, open(vcf, "w") as g:
+            g.writelines(f.readlines()[:first_records])
+        gold_cut = os.path.join(str(tmp_path), "golden_cut.vapor")
+        with open(gold) as f, open(gold_cut, "w") as g:
+            lines = f.readlines()
+            head = 1 if lines and not lines[0].strip() else 0         # the reference writes an empty header block first
+            g.writelines(lines[:first_records + head])
+        gold = gold_cut
+    else:
+        shutil.copy(os.path.join(case, "svs_nohdr.vcf"), vcf)
     args = Args(sv_input=vcf, output_path=os.path.join(str(tmp_path), "figs"), output_file="unused",
-                reference=os.path.join(CASE, "ref.fa"), pacbio_input=os.path.join(CASE, "reads.sam.gz"))
+                reference=os.path.join(case, "ref.fa"), pacbio_input=os.path.join(case, "reads.sam.gz"))
     SF.set_session(session)
     try:
         cli.run_vcf(args, [session])
     finally:
         SF.set_session(None)
-    compare_annotated_vcf(vcf + ".vapor", os.path.join(CASE, "svs_nohdr.vcf.vapor.golden"))
+    compare_annotated_vcf(vcf + ".vapor", gold)
 
 
 def run_disdup_case(session):

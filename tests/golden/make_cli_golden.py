@@ -124,6 +124,45 @@ def main():
     for f in sorted(os.listdir(CASE)):
         print(f, os.path.getsize(os.path.join(CASE, f)))
     make_large_case()
+    make_complex_case()
+
+
+def make_complex_case():
+    """Third case, vcf only: 56 complex events -- DEL_INV, DUP_INV, DEL_DUP_INV (two alternative haplotypes, README.md:81),
+    swapped blocks, two- and three-allele `Other=` records, and events of 10-11 kb that send vapor_CANNOT_CLASSIFY_VapoR
+    down its junction-window fallback (Simple_function.pyx:1537-1555).  DISDUP records are left out: the reference CLI
+    cannot process them under Python 3 (TypeError, :1803; disdup.golden.json of the first case pins that driver)."""
+    from vapor_b200 import synth_genome
+    case = os.path.join(HERE, "cli_case_complex")
+    if os.path.isdir(case):
+        shutil.rmtree(case)
+    kinds = ("DEL_INV", "DUP_INV", "DEL_DUP_INV", "OTHER", "OTHER2", "OTHER3", "DUP_INV", "DEL_DUP_INV", "OTHER3", "DEL_INV",
+             "OTHER2", "OTHER", "OTHER3", "OTHER_LONG")
+    ds = synth_genome.make_dataset(case, seed=20261018 + 3, n_simple=0, n_complex=56, size_range=(150, 700), coverage=20.0,
+                                   read_len_mean=5000.0, complex_types=kinds, kind_size={"OTHER_LONG": (7200, 7600)})
+    with open(ds.sam, "rb") as f, gzip.GzipFile(ds.sam + ".gz", "wb", mtime=0) as g:
+        shutil.copyfileobj(f, g)
+    os.remove(ds.sam)
+    os.remove(ds.bed)
+    sam = ds.sam + ".gz"
+    nohdr = os.path.join(case, "svs_nohdr.vcf")
+    with open(ds.vcf) as f, open(nohdr, "w") as g:
+        for line in f:
+            if not line.startswith("#"):
+                g.write(line)
+    os.remove(ds.vcf)
+    tmp = tempfile.mkdtemp(prefix="vapor_ref_cli_")
+    try:
+        env = _reference_env(tmp)
+        work_vcf = os.path.join(tmp, "svs_nohdr.vcf")
+        shutil.copy(nohdr, work_vcf)
+        subprocess.run([sys.executable, os.path.join(REF_PKG, "vapor"), "vcf", "--sv-input", work_vcf, "--output-path", os.path.join(tmp, "figs"),
+                        "--output-file", "unused", "--reference", ds.ref_fa, "--pacbio-input", sam], check=True, env=env, cwd=tmp)
+        shutil.copy(work_vcf + ".vapor", os.path.join(case, "svs_nohdr.vcf.vapor.golden"))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    for f in sorted(os.listdir(case)):
+        print("complex/" + f, os.path.getsize(os.path.join(case, f)))
 
 
 def make_large_case():
@@ -175,4 +214,7 @@ def _reference_env(tmp):
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "complex":
+        make_complex_case()
+    else:
+        main()

@@ -34,6 +34,15 @@ def test_vcf_cli_matches_reference_golden(tmp_path, session):
     CC.run_vcf_case(tmp_path, session)
 
 
+def test_vcf_cli_complex_events_match_reference_golden(tmp_path, session):
+    (tmp_path / "cut").mkdir()
+    """tests/golden/cli_case_complex: DEL_INV, DUP_INV, DEL_DUP_INV (two alternative haplotypes), swapped blocks, two- and
+    three-allele `Other=` records and a >= 10 kb event on the junction-window fallback, against the annotated VCF the
+    unmodified reference CLI wrote (56 records; the GPU suite repeats it with the real engine)."""
+    CC.run_vcf_case(tmp_path, session, CC.CASE_COMPLEX)
+    CC.run_vcf_case(tmp_path / "cut", session, CC.CASE_COMPLEX, first_records=3)      # a prefix of the file gives a prefix of the table
+
+
 def test_disdup_driver_matches_reference_golden(session):
     CC.run_disdup_case(session)
 

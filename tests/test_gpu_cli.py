@@ -38,6 +38,12 @@ def test_vcf_cli_matches_reference_golden(tmp_path, session):
     CC.run_vcf_case(tmp_path, session)
 
 
+def test_vcf_cli_complex_events_match_reference_golden(tmp_path, session):
+    """All 56 complex events of tests/golden/cli_case_complex (DEL_INV, DUP_INV, DEL_DUP_INV, swapped blocks, two- and
+    three-allele `Other=` records, junction-window fallbacks of >= 10 kb events) against the reference CLI's annotated VCF."""
+    CC.run_vcf_case(tmp_path, session, CC.CASE_COMPLEX)
+
+
 def test_disdup_driver_matches_reference_golden(session):
     CC.run_disdup_case(session)
 

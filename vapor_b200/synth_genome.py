@@ -141,14 +141,20 @@ def make_dataset(out_dir: str, seed: int = 20261018, n_simple: int = 8, n_comple
                  err: float = 0.15, chrom: str = "chr1", spacing: int = 3000, line_width: int = 60,
                  simple_types: Sequence[str] = ("DEL", "DUP", "INV", "INS"),
                  complex_types: Sequence[str] = ("DEL_INV", "DUP_INV", "DISDUP", "OTHER"),
-                 ins_with_seq_every: int = 2, het_frac: float = 0.5, ins_len_override: int = 0) -> Dataset:
-    """Write ref.fa(.fai), reads.sam, svs.bed, svs.vcf, truth.json under ``out_dir``."""
+                 ins_with_seq_every: int = 2, het_frac: float = 0.5, ins_len_override: int = 0,
+                 kind_size: Optional[Dict[str, Tuple[int, int]]] = None) -> Dataset:
+    """Write ref.fa(.fai), reads.sam, svs.bed, svs.vcf, truth.json under ``out_dir``.
+    ``kind_size``: per event kind, its own size range (e.g. a >= 10 kb ``OTHER_LONG`` event that sends the complex
+    driver down its junction-window fallback, Simple_function.pyx:1537-1555)."""
     rng = np.random.default_rng(seed)
     os.makedirs(out_dir, exist_ok=True)
     n_sv = n_simple + n_complex
     lens = rng.integers(size_range[0], size_range[1] + 1, size=n_sv)
     kinds = [simple_types[i % len(simple_types)] for i in range(n_simple)] + \
             [complex_types[i % len(complex_types)] for i in range(n_complex)]
+    for i, k_ in enumerate(kinds):
+        if kind_size and k_ in kind_size:
+            lens[i] = int(rng.integers(kind_size[k_][0], kind_size[k_][1] + 1))
     # each event owns a stretch: spacing + up to 3 blocks of its size + spacing
     lead = 12000                                                  # room for reads to start upstream of the first window
     starts = []
@@ -197,7 +203,22 @@ def make_dataset(out_dir: str, seed: int = 20261018, n_simple: int = 8, n_comple
             seg = [("ref", s, p), ("ins", ref[s:e].copy())]
             sv = PlantedSV(svid, kind, chrom, s, e, gt, extra={"insert_point": p})
             span_end = p
-        elif kind == "OTHER":                                      # ab -> ba : blocks swapped
+        elif kind == "DEL_DUP_INV":                                # README.md:81  ab/ab_a/bb^ : haplotype A = a, haplotype B = b b^
+            m_ = s + L
+            e = m_ + max(80, L // 2)
+            seg = [("del", s, m_), ("ref", m_, e), ("ins", _revcomp(ref[m_:e]))]
+            seg_a = [("ref", s, m_), ("del", m_, e)]
+            sv = PlantedSV(svid, kind, chrom, s, e, 2, extra={"bps": [s, m_, e], "ref": "ab", "alt": "a/bb^"})
+            span_end = e
+        elif kind == "OTHER3":                                     # three blocks, three alternative alleles: ac / ab^c / cba
+            m1 = s + L
+            m2 = m1 + max(80, L // 2)
+            e = m2 + max(80, L // 3)
+            seg = [("ref", s, m1), ("inv", m1, m2), ("ref", m2, e)]                      # haplotype B: a b^ c
+            seg_a = [("ref", s, m1), ("del", m1, m2), ("ref", m2, e)]                    # haplotype A: a c
+            sv = PlantedSV(svid, kind, chrom, s, e, 2, extra={"bps": [s, m1, m2, e], "ref": "abc", "alt": "ac/ab^c/cba"})
+            span_end = e
+        elif kind in ("OTHER", "OTHER_LONG"):                      # ab -> ba : blocks swapped
             m_ = s + L
             e = m_ + max(80, L // 2)
             seg = [("del", s, m_), ("ref", m_, e), ("ins", ref[s:m_].copy())]
@@ -213,7 +234,7 @@ def make_dataset(out_dir: str, seed: int = 20261018, n_simple: int = 8, n_comple
         else:
             raise ValueError(kind)
         svs.append(sv)
-        per_sv_segments.append((s, span_end, seg, seg_a if kind == "OTHER2" else None))
+        per_sv_segments.append((s, span_end, seg, seg_a if kind in ("OTHER2", "DEL_DUP_INV", "OTHER3") else None))
     # haplotypes: A carries hom-alt events only, B carries every event
     def build(which):
         segs, cur = [], 0
@@ -300,6 +321,13 @@ def make_dataset(out_dir: str, seed: int = 20261018, n_simple: int = 8, n_comple
             elif sv.svtype == "OTHER2":
                 b0, b1, b2 = sv.extra["bps"]
                 info = f"SVTYPE=cannot_classify_for_now;END={sv.end};Other=ab/ab_a/ba_{c}:{b0}:{b1}:{b2}"
+            elif sv.svtype == "DEL_DUP_INV":
+                b0, b1, b2 = sv.extra["bps"]
+                info = (f"SVTYPE=del_dup_inv;END={sv.end};del={c}:{b0}-{b1};dup_inv={c}:{b1}-{b2};insert_point={c}:{b2};"
+                        f"Other=ab/ab_a/bb^_{c}:{b0}:{b1}:{b2}")
+            elif sv.svtype == "OTHER3":
+                b0, b1, b2, b3 = sv.extra["bps"]
+                info = f"SVTYPE=cannot_classify_for_now;END={sv.end};Other=abc/abc_ac/ab^c/cba_{c}:{b0}:{b1}:{b2}:{b3}"
             else:
                 b0, b1, b2 = sv.extra["bps"]
                 info = f"SVTYPE=cannot_classify_for_now;END={sv.end};Other=ab/ab_ab/ba_{c}:{b0}:{b1}:{b2}"
