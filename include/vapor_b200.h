@@ -184,7 +184,9 @@ int vapor_host_plan(const vapor_batch_t* in, int k2_mode, int threads, int64_t w
  * which = 0: 32-bit compare-accumulate (ISETP) lane-ops/s, 1: LOP3 lane-ops/s, 2: IADD3 lane-ops/s (alu pipe alone),
  * 3: independent LOP3 + IMAD streams (alu pipe + fma pipe together: the dual-pipe integer issue rate the tile
  * kernel's inner loop is written for), 4: the tile kernel's inner loop in isolation (14 ISETP + 16 IMAD + 2 zero tests
- * per shared word, LDS.128 + one vote per 32 words, nothing else): integer lane-instructions/s. */
+ * per shared word, LDS.128 + one vote per 32 words, nothing else): integer lane-instructions/s,
+ * 5: IMAD lane-ops/s (fma pipe alone), 6: independent ISETP + IMAD streams with the streamed operand first -- the tile
+ * kernel's instruction mix without any of its structure (the non-circular dual-pipe ceiling). */
 int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s);
 
 /* The hit checksum mixer (host-callable; same function the kernels use). */

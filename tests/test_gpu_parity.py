@@ -127,6 +127,30 @@ def test_overflowing_waves_then_second_run(engine):
         np.testing.assert_array_equal(getattr(second, f), getattr(first, f), err_msg=f)
 
 
+def test_overflow_after_a_larger_batch(engine):
+    """A plot that overflows its first-pass capacity is incomplete -- with self-reverse-complement k-mers (two slots per
+    dot) the last slot before the capacity may never be written -- so kernel 3 must not look at it before the re-run:
+    after a batch with larger coordinates the stale slab contents would index outside the small plot's bitmaps
+    (found in round 2 as a timing-dependent illegal address)."""
+    rng = np.random.default_rng(31)
+    big = synth.make_workload(3, seed=5, types=("TANDUP",), size_range=(4000, 5000), reads_per_sv=4)
+    engine.score(big.batch)                                   # fills the hit slab with coordinates up to ~11 000
+    b = Batch()
+    for rep in (40, 75, 120):                                 # ACGT repeats: every 10-mer window is one of four, two of them palindromic
+        ref = np.concatenate([synth.random_dna(rng, 60), np.frombuffer(b"ACGT" * rep, np.uint8), synth.random_dna(rng, 60)])
+        alt = np.concatenate([ref[:80], np.frombuffer(b"ACGT" * (rep // 2), np.uint8), ref[-70:]])
+        rid, aid = b.add_seq(ref), b.add_seq(alt)
+        for mode in (MODE_ABS, MODE_W10, MODE_REDEF, MODE_ABS_AND_W10):
+            b.add_task(b.add_seq(ref[10:-10]), rid, aid, 0, 10, mode)
+        b.end_sv(rep)
+    pb = b.pack()
+    exp = BO.score_batch(pb)
+    for _ in range(4):
+        res = engine.score(pb)
+        assert engine.timings()["n_overflow_plots"] > 0
+        _compare(res, exp)
+
+
 def test_negative_miss_bp_slices_from_the_end(engine):
     """cigar2alignstart_by_pos can hand back a negative miss_bp; the reference then slices ref_seq[miss_bp:] the
     Python way (Simple_function.pyx:185-186).  The library does the same instead of rejecting the batch."""

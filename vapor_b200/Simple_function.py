@@ -396,6 +396,9 @@ def simple_chop_pacbio_read_simple_short(bam_in, sv_info, flank_length):
 # ====================================================================================================
 # requests a driver coroutine yields, and the session that answers them on the GPU
 # ====================================================================================================
+XMEANS_ON_HOST = os.environ.get("VAPOR_XMEANS", "1") != "0"     # 0: size the below-diagonal dots by one bounding box
+
+
 class RefineRequest:
     """``window_size_refine(seq)``: answered with ``[window_size, region_QC]`` or ``['Error', 'Error']``."""
     __slots__ = ("seq", "region_QC_Cff")
@@ -489,7 +492,14 @@ class Session:
                     # (Simple_function.pyx:1170) -- reported as an unusable window too
                     out[i] = ["Error", "Error"]
                     continue
-                region_qc = _qual_check_from_counts(row, len(seqs[i]))
+                lower_dots = None
+                if 0.1 < float(row[2]) / float(H) < 0.5 and float(row[1]) / float(H) <= reqs[i].region_QC_Cff and XMEANS_ON_HOST:
+                    # repeat-rich window: its below-diagonal dots, from the GPU, sized by the reference's X-means on the host
+                    d = self.engine.dotdata(k[i], seqs[i], seqs[i])
+                    self.stats["gpu_calls"] += 1
+                    low = d[d[:, 0] > d[:, 1]]
+                    lower_dots = (low[:, 0].tolist(), low[:, 1].tolist())
+                region_qc = _qual_check_from_counts(row, len(seqs[i]), lower_dots)
                 if k[i] > 30 or region_qc[0] > reqs[i].region_QC_Cff or sum(region_qc[1]) / float(len(seqs[i])) < 0.3:
                     out[i] = [k[i], region_qc]
                 else:
@@ -573,21 +583,98 @@ class Session:
         return out
 
 
-def _qual_check_from_counts(row, seq_len):
+def _qual_check_from_counts(row, seq_len, lower_dots=None):
     """``qual_check_repetitive_region`` (Simple_function.pyx:1154-1171) from the self-plot counters.
 
-    The diagonal fraction is exact.  When 10-50 % of the dots lie below the diagonal the reference clusters
-    them with an unseeded scikit-learn KMeans inside a recursive X-means (:856-906, :2101-2116) and takes
-    sqrt(box area) per cluster; that path is not deterministic and calls ``scipy.std``, which current SciPy
-    no longer has, so it cannot be pinned.  Here the dots below the diagonal count as one cluster (their
-    bounding box) -- documented in DESIGN.md as the one place k selection is parity-unpinned."""
+    The diagonal fraction is exact.  When 10-50 % of the dots lie below the diagonal the reference sizes them with a
+    recursive X-means (:856-906, :2101-2116): ``lower_dots`` = (x list, y list) of those dots lets ``xmeans_box_sizes``
+    restate that; without them the dots count as one cluster (their bounding box)."""
     H, diag, lower = int(row[0]), int(row[1]), int(row[2])
     frac = float(lower) / float(H)
     if 0.1 < frac < 0.5:
-        size_cluster = [float(np.sqrt((int(row[4]) - int(row[3])) * (int(row[6]) - int(row[5]))))]
+        if lower_dots is not None:
+            size_cluster = xmeans_box_sizes(lower_dots[0], lower_dots[1])
+        else:
+            size_cluster = [float(np.sqrt((int(row[4]) - int(row[3])) * (int(row[6]) - int(row[5]))))]
     else:
         size_cluster = [0]
     return [float(diag) / float(H), size_cluster]
+
+
+# ---- the reference's X-means sizing of the below-diagonal dots (host; only repeat-rich windows get here) ---------
+def _bic(km, X):
+    """compute_bic (Simple_function.pyx:480-516) with its clusters-with-negative-variance filter (:518-525)."""
+    from scipy.spatial import distance
+    centers, labels, m = km.cluster_centers_, km.labels_, km.n_clusters
+    n = np.bincount(labels)
+    N, d = X.shape
+    var = []
+    for i in range(m):
+        sq = sum(distance.cdist(X[np.where(labels == i)], [centers[i]], "euclidean") ** 2)
+        var.append((1.0 / (n[i] - m)) * sq if n[i] - m != 0 else float(10 ** 20) * sq)
+    const_term = 0.5 * m * np.log10(N)
+    keep = []
+    for i in range(m):
+        var[i] = [0.0 if v == -0.0 else v for v in var[i]]
+        if not any(v < 0 for v in var[i]):
+            keep.append(i)
+    return np.sum([n[i] * np.log10(n[i]) - n[i] * np.log10(N) - ((n[i] * d) / 2) * np.log10(2 * np.pi) -
+                   (n[i] / 2) * np.log10(var[i]) - ((n[i] - m) / 2) for i in keep]) - const_term
+
+
+def _kmeans_split(xs, ys):
+    """k_means_cluster (Simple_function.pyx:856-889): 1-4 clusters by scikit-learn KMeans, the count chosen by BIC, the
+    split itself by scipy's whitened kmeans.  The library calls are made in the reference's order, so with the same
+    numpy random state the split is the same."""
+    from scipy.cluster.vq import kmeans, vq, whiten
+    from sklearn import cluster
+    if not (max(xs) - min(xs) > 10 and max(ys) - min(ys) > 10):
+        return [(xs, ys)]
+    pts = np.array([[xs[i], ys[i]] for i in range(len(xs))])
+    ks = list(range(1, min(5, len(xs) + 1)))
+    fits = [cluster.KMeans(n_clusters=i, init="k-means++").fit(pts) for i in ks]
+    preds = [cluster.KMeans(n_clusters=i, init="k-means++").fit_predict(pts) for i in ks]
+    bic, bic_k = [], []
+    for k in ks:
+        if preds[k - 1].max() < k - 1:
+            continue
+        b = _bic(fits[k - 1], pts)
+        if abs(b) < 10 ** 8:
+            bic.append(b); bic_k.append(k)
+    picked = bic_k[bic.index(max(bic))]
+    if picked == 1:
+        return [(xs, ys)]
+    white = whiten(pts)
+    centroids, _ = kmeans(white, picked)
+    idx, _ = vq(white, centroids)
+    return [([int(v) for v in pts[idx == c, 0]], [int(v) for v in pts[idx == c, 1]]) for c in range(picked)]
+
+
+def _xmeans(xs, ys):
+    """X_means_cluster (Simple_function.pyx:2101-2109): split until a part no longer splits."""
+    parts = [p for p in _kmeans_split(xs, ys) if not (p[0] == [] and p[1] == [])]
+    if len(parts) == 1 and parts[0][0] == xs and parts[0][1] == ys:
+        return [(xs, ys)]
+    out = []
+    for px, py in parts:
+        out += _xmeans(px, py)
+    return out
+
+
+def xmeans_box_sizes(xs, ys):
+    """sqrt(bounding-box area) of every X-means cluster of the dots (x, y) below the diagonal
+    (X_means_cluster_reformat, cluster_range_decide, cluster_size_decide: Simple_function.pyx:2110-2116, 372-385).
+    The clustering draws from numpy's global random state exactly like the reference; a window the libraries cannot
+    cluster (the reference would raise) falls back to one bounding box."""
+    xs, ys = [int(v) for v in xs], [int(v) for v in ys]
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            clusters = _xmeans(xs, ys)
+    except Exception:                                   # noqa: BLE001
+        clusters = [(xs, ys)]
+    return [float(np.sqrt((max(cx) - min(cx)) * (max(cy) - min(cy)))) for cx, cy in clusters]
 
 
 _session: Optional[Session] = None
@@ -637,7 +724,7 @@ def qual_check_repetitive_region(dotdata_qual_check):
     row = [H, sum(1 for x, y in dotdata_qual_check if x == y), len(low),
            min((x for x, _ in low), default=0), max((x for x, _ in low), default=0),
            min((y for _, y in low), default=0), max((y for _, y in low), default=0)]
-    return _qual_check_from_counts(row, 0)
+    return _qual_check_from_counts(row, 0, ([x for x, _ in low], [y for _, y in low]) if XMEANS_ON_HOST else None)
 
 
 def window_size_refine(seq2, region_QC_Cff=region_QC_Cff_default):

@@ -93,6 +93,7 @@ struct Handle {
     int k2_mode = 1;                 // 0 = all-pairs tile kernel (k2_tile.cuh), 1 = join kernel (k2_join.cuh)
     int plan_mode = 1;               // mode the resident plan was made for
     int plan_threads = 0;            // host threads for planning (0 = auto)
+    int debug_sync = getenv("VAPOR_DEBUG_SYNC") ? atoi(getenv("VAPOR_DEBUG_SYNC")) : 0;   // bit mask: 1 k1, 2 k1b, 4 k2, 8 k3
 
     // plan (host)
     std::vector<Operand> ops;
@@ -952,6 +953,15 @@ int redo_wave(Handle* h, size_t wi, int64_t* launches) {
     return rc;
 }
 
+// VAPOR_DEBUG_SYNC=1: synchronise after every launch so that a device fault names the kernel that raised it
+#define CKL(name, bit)                                                                                \
+    do {                                                                                              \
+        if (h->debug_sync & (bit)) {                                                                        \
+            cudaError_t e_ = cudaStreamSynchronize(h->stream);                                        \
+            if (e_ != cudaSuccess) { h->err = std::string(name) + ": " + cudaGetErrorString(e_); return VAPOR_E_CUDA; } \
+        }                                                                                             \
+    } while (0)
+
 int run_impl(Handle* h) {
     if (!h->resident) { h->err = "no resident batch: call vapor_gpu_upload first"; return VAPOR_E_STATE; }
     CK(cudaSetDevice(h->device));
@@ -974,12 +984,14 @@ int run_impl(Handle* h) {
         sp = span_begin(h, CAT_PACK);
         launches += launch_k1_wave(h, w);
         span_end(h, sp);
+        CKL("k1_pack_kmers", 1);
         if (h->plan_mode == 1 && w.chunk_end > w.chunk_begin) {
             sp = span_begin(h, CAT_TABLE);
             k1b_build_tables<<<(unsigned)(w.chunk_end - w.chunk_begin), K1B_THREADS, 0, h->stream>>>(
                 h->d_chunks.p + w.chunk_begin, h->d_ops.p, h->d_hash.p, h->d_table.p);
             ++launches;
             span_end(h, sp);
+            CKL("k1b_build_tables", 2);
         }
         CK(cudaGetLastError());
         // ---- kernel 2 ---------------------------------------------------------------------
@@ -1015,6 +1027,7 @@ int run_impl(Handle* h) {
         }
         span_end(h, sp);
         CK(cudaGetLastError());
+        CKL("kernel 2", 4);
         // ---- kernel 3, one launch per scratch class ----------------------------------------------
         sp = span_begin(h, CAT_SCORE);
         for (int c = 0; c < K3_NCLASS; ++c) {
@@ -1028,6 +1041,7 @@ int run_impl(Handle* h) {
             kp.task_hits = h->d_task_hits.p; kp.task_hitsum = h->d_task_hitsum.p;
             launch_k3_class(h, kp, c, h->max_nb);
             ++launches;
+            CKL("k3_score_reads", 8);
         }
         span_end(h, sp);
         CK(cudaGetLastError());
@@ -1154,6 +1168,34 @@ __global__ void __launch_bounds__(256) k_int_peak(const uint32_t* __restrict__ i
         #pragma unroll
         for (int q = 0; q < 32; ++q) a ^= r[q];
         if (a == 0x12345678u) out[0] = a;
+    } else if (WHICH == 5) {
+        // fma pipe alone: 32 independent IMAD chains, the streamed word first
+        for (int it = 0; it < iters; ++it) {
+            #pragma unroll
+            for (int q = 0; q < 32; ++q) r[q] = v * r[q] + r[(q + 3) & 31];
+            v += 0x9E3779B9u;
+        }
+        uint32_t a = 0;
+        #pragma unroll
+        for (int q = 0; q < 32; ++q) a ^= r[q];
+        if (a == 0x12345678u) out[0] = a;
+    } else if (WHICH == 6) {
+        // both pipes, the instruction mix of the tile kernel but none of its structure: 16 independent compare-accumulates
+        // (ISETP, alu pipe) + 16 independent multiply-adds (IMAD, fma pipe) per step, the streamed word first in each
+        bool p0 = false, p1 = false, p2 = false, p3 = false;
+        for (int it = 0; it < iters; ++it) {
+            #pragma unroll
+            for (int q = 0; q < 16; q += 4) {
+                p0 |= (v == r[q]); p1 |= (v == r[q + 1]); p2 |= (v == r[q + 2]); p3 |= (v == r[q + 3]);
+            }
+            #pragma unroll
+            for (int q = 16; q < 32; ++q) r[q] = v * r[q] + r[16 + ((q + 3) & 15)];
+            v += 0x9E3779B9u;
+        }
+        uint32_t a = 0;
+        #pragma unroll
+        for (int q = 16; q < 32; ++q) a ^= r[q];
+        if ((p0 | p1 | p2 | p3) && a == 0x12345678u) out[0] = a;
     } else {
         for (int it = 0; it < iters; ++it) {
             #pragma unroll
@@ -1571,7 +1613,7 @@ int vapor_host_plan(const vapor_batch_t* in, int k2_mode, int threads, int64_t w
 }
 
 int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s) {
-    if (!handle || !lane_ops_per_s || which < 0 || which > 4) return VAPOR_E_ARG;
+    if (!handle || !lane_ops_per_s || which < 0 || which > 6) return VAPOR_E_ARG;
     Handle* h = static_cast<Handle*>(handle);
     CK(cudaSetDevice(h->device));
     DevBuf<uint32_t> in, out;
@@ -1589,6 +1631,8 @@ int vapor_gpu_int_peak(void* handle, int which, double* lane_ops_per_s) {
         if (which == 0) k_int_peak<0><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         else if (which == 1) k_int_peak<1><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         else if (which == 3) k_int_peak<3><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
+        else if (which == 5) k_int_peak<5><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
+        else if (which == 6) k_int_peak<6><<<grid, 256, 0, h->stream>>>(in.p, out.p, iters);
         else if (which == 4) {
             const int g4 = h->sm_count * 4, reps = 48;
             k_tile_loop_peak<<<g4, 128, 0, h->stream>>>(in.p, out.p, reps);

@@ -59,6 +59,7 @@ struct K3Shared {       // block-wide accumulators (static shared memory)
     int m2min, m2max;
     long long icpt2;    // twice the intercept
     unsigned int warp_tot[K3_THREADS / 32];
+    unsigned int warp_tot2[K3_THREADS / 32];
 };
 
 __device__ __forceinline__ void k3_setup_scratch(K3Scratch& s, uint32_t* base, int nb_cap) {
@@ -94,6 +95,29 @@ __device__ void k3_block_scan(uint32_t* arr, int N, K3Shared& sh) {
     for (int w = 0; w < warp; ++w) base += sh.warp_tot[w];
     uint32_t run = base + inc - sum;
     for (int i = b0; i < b1; ++i) { run += arr[i]; arr[i] = run; }
+    __syncthreads();
+}
+
+// The same for two arrays of the same length at once (the y-x and y+x group sets): one pair of barriers instead of two.
+__device__ void k3_block_scan2(uint32_t* a0, uint32_t* a1, int N, K3Shared& sh) {
+    const int tid = threadIdx.x, T = K3_THREADS;
+    int C = (N + T - 1) / T;
+    C |= 1;
+    const int b0 = min(tid * C, N), b1 = min(b0 + C, N);
+    uint32_t s0 = 0, s1 = 0;
+    for (int i = b0; i < b1; ++i) { s0 += a0[i]; s1 += a1[i]; }
+    uint32_t i0 = s0, i1 = s1;
+    const int lane = tid & 31, warp = tid >> 5;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v0 = __shfl_up_sync(0xFFFFFFFFu, i0, o), v1 = __shfl_up_sync(0xFFFFFFFFu, i1, o);
+        if (lane >= o) { i0 += v0; i1 += v1; }
+    }
+    if (lane == 31) { sh.warp_tot[warp] = i0; sh.warp_tot2[warp] = i1; }
+    __syncthreads();
+    uint32_t r0 = i0 - s0, r1 = i1 - s1;
+    for (int w = 0; w < warp; ++w) { r0 += sh.warp_tot[w]; r1 += sh.warp_tot2[w]; }
+    for (int i = b0; i < b1; ++i) { r0 += a0[i]; a0[i] = r0; r1 += a1[i]; a1[i] = r1; }
     __syncthreads();
 }
 
@@ -239,8 +263,7 @@ __device__ void k3_build_groups_both(const PlotView& v, K3Scratch& s, K3Shared& 
     k3_groups_starts(s.D, W);
     k3_groups_starts(s.A, W);
     __syncthreads();
-    k3_block_scan(s.D.wpref + 1, W, sh);
-    k3_block_scan(s.A.wpref + 1, W, sh);
+    k3_block_scan2(s.D.wpref + 1, s.A.wpref + 1, W, sh);
     const int ngD = (int)s.D.wpref[W], ngA = (int)s.A.wpref[W];
     for (int g = tid; g < ngD; g += K3_THREADS) s.D.gsize[g] = 0u;
     for (int g = tid; g < ngA; g += K3_THREADS) s.A.gsize[g] = 0u;
@@ -355,7 +378,8 @@ __device__ void k3_clean_w10(const PlotView& v, K3Scratch& s, K3Shared& sh, Plot
 // and everything lands in the last bin when range == 0.
 __device__ __forceinline__ int k3_bin11(int d, int mn, int range) {
     if (range <= 0) return 10;
-    return (int)((10ll * (long long)(d - mn)) / (long long)range);
+    // d - mn <= range < 2^28 (sequence lengths are below 2^27), so 10 (d - mn) fits 32 unsigned bits: one 32-bit division
+    return (int)((10u * (uint32_t)(d - mn)) / (uint32_t)range);
 }
 
 // dis_to_diagnal_most_abundant_defined + eu_dis_dir_calcu on the clean dots (Simple_function.pyx:582-591,
@@ -444,16 +468,18 @@ __device__ void k3_redef_stat(const PlotView& v, K3Scratch& s, K3Shared& sh, Plo
                 }
             }
             __syncthreads();
-            if (tid == 0) {
+            // np.median of the sub-bin: the values of rank (c-1)/2 and c/2, found on the inclusive prefix of the value counts
+            k3_block_scan(s.aux, rg2 + 1, sh);
+            {
                 const uint32_t r0 = (c - 1) / 2, r1 = c / 2;
-                uint32_t cum = 0; int v0 = -1, v1 = -1;
-                for (int t = 0; t <= rg2 && v1 < 0; ++t) {
-                    cum += s.aux[t];
-                    if (v0 < 0 && cum > r0) v0 = t;
-                    if (cum > r1) v1 = t;
+                for (int t = tid; t <= rg2; t += K3_THREADS) {
+                    const uint32_t lo = t ? s.aux[t - 1] : 0u, hi = s.aux[t];
+                    if (lo <= r0 && hi > r0) sh.m2min = t;                 // m2min / m2max are free again: reused for the two ranks
+                    if (lo <= r1 && hi > r1) sh.m2max = t;
                 }
-                sh.icpt2 = (long long)(v0 + mn2) + (long long)(v1 + mn2);
             }
+            __syncthreads();
+            if (tid == 0) sh.icpt2 = (long long)(sh.m2min + mn2) + (long long)(sh.m2max + mn2);
             __syncthreads();
         }
     }
@@ -586,8 +612,10 @@ k3_score_reads(const K3Params p)
         for (int i = 0; i < 4; ++i) {
             if (t.plot[i] >= 0) {
                 const Plot pl = p.plots[t.plot[i]];
-                // a plot that overflowed its first-pass capacity holds only `cap` dots: its task is scored again by redo_wave
-                pv[i].hits = p.hits + pl.hit_off; pv[i].H = min(p.cnt[t.plot[i]], pl.cap); pv[i].n = pl.n; pv[i].m = pl.m;
+                // a plot that overflowed its first-pass capacity is incomplete (slots near the end of its list may never have
+                // been written): it counts as empty here, and its task is scored again by redo_wave with the exact capacity
+                const uint32_t found = p.cnt[t.plot[i]];
+                pv[i].hits = p.hits + pl.hit_off; pv[i].H = found > pl.cap ? 0u : found; pv[i].n = pl.n; pv[i].m = pl.m;
             } else { pv[i].hits = nullptr; pv[i].H = 0; pv[i].n = 0; pv[i].m = 0; }
         }
         const bool bad = p.op_status[t.read_op] != 0;
