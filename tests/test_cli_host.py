@@ -97,3 +97,18 @@ def test_svelter_subcommand_matches_vcf_other_path(tmp_path, session):
     gold = [l.rstrip("\n").split("\t") for l in open(os.path.join(CC.CASE, "svs_nohdr.vcf.vapor.golden")) if "<OTHER>" in l][0]
     rec = [kv for kv in gold[7].split(";") if kv.startswith("VaPor_REC=")][0].split("=", 1)[1]
     assert row[0] == f".chr1_{b0}_{b1}_{b2}" and row[-1] == rec
+
+
+def test_kselect_on_repeat_rich_windows_matches_reference_golden(session):
+    """window_size_refine on windows with planted tandem / inverted / interspersed repeats: the k the unmodified reference
+    chose (tests/golden/kselect_cases.json, numpy's random state seeded as recorded -- its X-means is otherwise unseeded;
+    36 of the 48 windows reach the X-means sizing of the below-diagonal dots, Simple_function.pyx:1154-1171, 856-906,
+    2101-2116).  profiles/r02_kselect_agreement.json holds the same comparison on 2 000 windows (100 % agreement)."""
+    import json
+    import numpy as np
+    cases = json.load(open(os.path.join(CC.HERE, "golden", "kselect_cases.json")))["cases"]
+    assert sum(1 for c in cases if c["xmeans_branch_at_k10"]) >= 30
+    for c in cases:
+        np.random.seed(c["seed"])
+        got = session.refine_many([SF.RefineRequest(c["seq"])])[0][0]
+        assert got == c["k"], (c["kind"], len(c["seq"]), got, c["k"])

@@ -164,3 +164,15 @@ def test_figure_hook_writes_png(tmp_path, session, monkeypatch):
     SF.vapor_simple_del_Vapor(3, 1, os.path.join(CC.CASE, "reads.sam.gz"), os.path.join(CC.CASE, "ref.fa"), ["chr1", 12000, 12643], fig)
     data = open(fig, "rb").read()
     assert data[:8] == b"\x89PNG\r\n\x1a\n" and len(data) > 1000
+
+
+def test_kselect_on_repeat_rich_windows_matches_reference_golden(session):
+    """The same 48 repeat-rich windows as the CPU suite, the self-plots and the below-diagonal dot lists from the GPU."""
+    import json
+    import os
+    import numpy as np
+    cases = json.load(open(os.path.join(CC.HERE, "golden", "kselect_cases.json")))["cases"]
+    for c in cases:
+        np.random.seed(c["seed"])
+        got = session.refine_many([SF.RefineRequest(c["seq"])])[0][0]
+        assert got == c["k"], (c["kind"], len(c["seq"]), got, c["k"])
