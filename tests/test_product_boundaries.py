@@ -28,7 +28,7 @@ def test_product_never_imports_the_oracle():
 def test_header_and_binding_agree():
     from vapor_b200 import _native
     hdr = open(os.path.join(ROOT, "include", "vapor_b200.h")).read()
-    declared = set(re.findall(r"\b(vapor_(?:gpu_\w+|hit_mix|b200_abi_version))\s*\(", hdr))
+    declared = set(re.findall(r"\b(vapor_(?:gpu_\w+|hit_mix|host_plan|b200_abi_version))\s*\(", hdr))
     assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
 
 
