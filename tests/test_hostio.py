@@ -286,3 +286,23 @@ def test_prefetch_cache_gives_the_same_answers(python_io):
         assert len(seqio.chop_reads([SAM], c, s, e, f)) == n
     seqio.clear_prefetch()
     assert not seqio._region_cache and not seqio._reads_cache
+
+
+def test_integration_md_hostio_stub_runs(python_io):
+    """The host-I/O ctypes stub INTEGRATION.md shows a maintainer of the reference, executed as written (only the library
+    path is made absolute), returns what the Python restatement of the reference's functions returns."""
+    import re
+    from vapor_b200 import _native
+    md = open(os.path.join(os.path.dirname(HERE), "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(# vapor_vali/_b200_io\.py.*?)```", md, re.S).group(1)
+    block = block.replace('C.CDLL("libvapor_b200.so")', f'C.CDLL({_native.LIB_PATH!r})')
+    ns = {}
+    exec(compile(block, "INTEGRATION.md:_b200_io.py", "exec"), ns)
+    fa, al = ns["open_fasta"](REF), ns["open_alignments"](SAM)
+    pf = seqio.FastaFile(REF)
+    chrom = pf.order[0]
+    assert ns["ref_seq_readin"](fa, chrom, 12000, 13200) == pf.fetch(chrom, 12000, 13200)
+    wins = [(chrom, 11500, 13143, 500), (chrom, 24214, 25980, 500), (chrom, 36064, 37064, 500)]
+    got = ns["chop_and_minimize"]([al], wins)
+    exp = [SF.minimize_pacbio_read_list(python_io(SF.chop_pacbio_read_by_pos, SAM, *w)) for w in wins]
+    assert got == exp and all(len(x) > 3 for x in got)
