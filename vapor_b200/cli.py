@@ -184,6 +184,21 @@ class Event:
         return getattr(SF, self.spec[0])(*self.spec[1])
 
 
+def _run_chunked(sess, specs, prefetch=True):
+    """Drive the coroutines of many events chunk by chunk; each chunk's primary region / read queries are answered
+    ahead in bulk by the native reader (bounded memory: 20 reads x a few kb per event)."""
+    out = []
+    for c0 in range(0, len(specs), EVENT_CHUNK):
+        chunk = specs[c0:c0 + EVENT_CHUNK]
+        if prefetch:
+            SF.prefetch_events(chunk)
+        res = sess.run_events([getattr(SF, name)(*a) for name, a in chunk])
+        out += [r if r is not None else [] for r in res]
+        if prefetch:
+            seqio.clear_prefetch()
+    return out
+
+
 def _shard_worker(job):
     """Worker process of the multi-GPU command line: one process per GPU, its own Session, its share of the events."""
     device, specs = job
@@ -191,11 +206,40 @@ def _shard_worker(job):
     sess = SF.Session(device % max(1, load().vapor_gpu_device_count()))      # more workers than GPUs: share them
     SF.set_session(sess)
     try:
-        res = sess.run_events([getattr(SF, name)(*a) for name, a in specs])
-        return [r if r is not None else [] for r in res], dict(sess.stats)
+        return _run_chunked(sess, specs), dict(sess.stats)
     finally:
         sess.close()
         SF.set_session(None)
+
+
+def event_cost(spec) -> int:
+    """Rough recurrence-cell cost of one event from its arguments alone (what the LPT partition of --gpus N balances)."""
+    from . import synth
+    name, a = spec
+    try:
+        if name in ("co_simple_del", "co_simple_inv", "co_simple_tandup"):
+            sv = a[4]
+            L = int(sv[2]) - int(sv[1])
+            if L >= SF.default_max_sv_test:
+                return 20 * 1000 * 2000
+            return synth.simple_cost({"co_simple_del": "DEL", "co_simple_inv": "INV", "co_simple_tandup": "TANDUP"}[name], max(L, 1), 10, 20)
+        if name == "co_simple_ins":
+            return synth.simple_cost("INS", max(len(a[5]), 1), 10, 20)
+        nums = [int(x) for x in _flatten(a[4]) if isinstance(x, int) or (isinstance(x, str) and x.isdigit())]
+        span = (max(nums) - min(nums)) if len(nums) >= 2 else 1000
+        if span >= SF.default_max_sv_test:
+            return 20 * 1000 * 2000
+        return 20 * (span + 1000) * 2 * (span + 1000) * 2
+    except Exception:                                   # noqa: BLE001
+        return 20 * 2000 * 4000
+
+
+def _flatten(x):
+    if isinstance(x, (list, tuple)):
+        for y in x:
+            yield from _flatten(y)
+    else:
+        yield x
 
 
 EVENT_CHUNK = 4000          # events whose drivers run (and whose reads are prefetched) together
@@ -212,11 +256,14 @@ def score_events(events: Sequence[Event], sessions) -> List[list]:
     if isinstance(sessions, int):
         n_s = sessions
         import multiprocessing as mp
-        jobs = [(d, [events[i].spec for i in live[d::n_s]]) for d in range(n_s)]
+        from . import multi
+        # the product's partitioner: greedy longest-processing-time on the events' cell estimates (multi.partition_svs)
+        parts = [[live[j] for j in p] for p in multi.partition_svs([event_cost(events[i].spec) for i in live], n_s)]
+        jobs = [(d, [events[i].spec for i in parts[d]]) for d in range(n_s)]
         with mp.get_context("fork").Pool(n_s) as pool:          # fork: the parsed FASTA index / SAM records are inherited
             outs = pool.map(_shard_worker, jobs, chunksize=1)
         for d, (lists, _stats) in enumerate(outs):
-            for i, r in zip(live[d::n_s], lists):
+            for i, r in zip(parts[d], lists):
                 score_lists[i] = r
         summ_session = SF.Session(0)
         try:
@@ -231,16 +278,9 @@ def score_events(events: Sequence[Event], sessions) -> List[list]:
             try:
                 SF.set_session(sessions[si], thread_only=True)   # figure hooks use the calling thread's session
                 mine = live[si::n_s]
-                # chunks bound the memory of the prefetched reads (20 reads x a few kb per event)
-                for c0 in range(0, len(mine), EVENT_CHUNK):
-                    idx = mine[c0:c0 + EVENT_CHUNK]
-                    if n_s == 1:
-                        SF.prefetch_events([events[i].spec for i in idx])
-                    res = sessions[si].run_events([events[i].make() for i in idx])
-                    for i, r in zip(idx, res):
-                        score_lists[i] = r if r is not None else []
-                    if n_s == 1:
-                        seqio.clear_prefetch()
+                # the prefetch cache is process-wide: used when one session drives everything (threads share the per-call route)
+                for i, r in zip(mine, _run_chunked(sessions[si], [events[i].spec for i in mine], prefetch=(n_s == 1))):
+                    score_lists[i] = r
             except BaseException as e:                  # noqa: BLE001
                 errs.append(e)
         if n_s == 1:
