@@ -501,8 +501,21 @@ def run_gpu_arm(args):
     dom = max(kernels, key=lambda n: kernels[n]["ms"])
     step_ms = acc["total_ms"] / K
     roofline = dict(kernels[dom])
+    # DRAM traffic of the dominant kernel: measured by ncu (dram__bytes_read + dram__bytes_write, summed over the kernel's launches
+    # of one run) on 2 000 SVs of config 2 -- quoted as `traffic` only when this run is that very workload, never scaled
+    traffic, traffic_profile = None, None
+    try:
+        tp = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        kt = tp["kernels"].get(dom)
+        if kt:
+            traffic_profile = {"measured_on": f"config {tp['config']}, {tp['n_sv']} SVs (ncu --set full)", "dram_bytes": kt["dram_bytes_read"] + kt["dram_bytes_write"],
+                               "launches": kt["launches"], "kernel_ms_under_ncu": kt["ms"]}
+            if args.config == tp["config"] and n_list == tp["n_sv"] and world == 1:
+                traffic = (kt["dram_bytes_read"] + kt["dram_bytes_write"]) / max(1, kt["launches"])
+    except Exception:
+        pass
     roofline.update({"kernel": dom, "share_of_step": kernels[dom]["ms"] / max(step_ms, 1e-9), "peak_source": kernels[dom].get("peak_source", hbm_src),
-                     "traffic": None, "traffic_note": "per-launch DRAM bytes from ncu are in profiles/ (captured at a smaller batch)"})
+                     "traffic": traffic, "traffic_profile": traffic_profile})
     if roofline["bound"] != "hbm":
         roofline["bound_schema"] = "integer issue (the schema's hbm|tensor does not apply: integer compare work)"
 
@@ -597,7 +610,7 @@ def main():
     ap.add_argument("--n-sv", type=int, default=0, help="SVs in the list (0 = the config's size); per GPU with --weak")
     ap.add_argument("--weak", action="store_true", help="every rank scores its own --n-sv SVs instead of a share of one list")
     ap.add_argument("--ref-svs", type=int, default=0, help="SVs per CPU sample (0 = sized from --ref-seconds)")
-    ap.add_argument("--ref-seconds", type=float, default=4.0, help="all-core seconds one reference-arm step should take")
+    ap.add_argument("--ref-seconds", type=float, default=10.0, help="all-core seconds one reference-arm step should take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tile-variant", type=int, default=-1, help="tile-kernel inner loop (-1 = library default)")
     ap.add_argument("--k2-mode", type=int, default=-1, help="kernel 2: 1 = join (library default), 0 = all-pairs tile kernel")
