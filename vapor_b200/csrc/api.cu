@@ -807,7 +807,8 @@ int launch_k2_join(Handle* h, const JoinPlan& jp, size_t wi, K2JParams kp) {
         const int64_t o0 = jp.item_off[wi * K2J_NCLASS + c], o1 = jp.item_off[wi * K2J_NCLASS + c + 1];
         if (o1 == o0) continue;
         kp.items = items0 + o0;
-        k2_join_match<<<(unsigned)(o1 - o0), K2J_THREADS, (size_t)k2j_class_cap[c], h->stream>>>(kp);
+        if (c == K2J_NCLASS - 1) k2_join_match<K2J_WARPS_BIG><<<(unsigned)(o1 - o0), 32 * K2J_WARPS_BIG, (size_t)k2j_class_cap[c], h->stream>>>(kp);
+        else                     k2_join_match<K2J_WARPS><<<(unsigned)(o1 - o0), 32 * K2J_WARPS, (size_t)k2j_class_cap[c], h->stream>>>(kp);
         ++launches;
     }
     return launches;
@@ -1301,7 +1302,8 @@ int vapor_gpu_open(int device, void** handle) {
     if (e != cudaSuccess) { g_open_error = std::string("kernel image not loadable on this device: ") + cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return VAPOR_E_CUDA; }
     e = cudaFuncSetAttribute(k3_score_reads, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(k3_scratch_words(k3_class_cap[K3_NCLASS - 2]) * sizeof(uint32_t)));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_join_match, cudaFuncAttributeMaxDynamicSharedMemorySize, k2j_class_cap[K2J_NCLASS - 1]);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_join_match<K2J_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2j_class_cap[K2J_NCLASS - 1]);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_join_match<K2J_WARPS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2j_class_cap[K2J_NCLASS - 1]);
     if (e != cudaSuccess) { g_open_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return VAPOR_E_CUDA; }
     e = cudaEventCreate(&h->ev_run0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev_run1);

@@ -26,8 +26,8 @@
 namespace vb {
 
 constexpr int K1B_THREADS = 256;
-constexpr int K2J_WARPS   = 8;
-constexpr int K2J_THREADS = 32 * K2J_WARPS;
+constexpr int K2J_WARPS     = 8;                // warps per CTA (tables up to 44 KB: 4 CTAs per SM)
+constexpr int K2J_WARPS_BIG = 16;               // ... for the largest tables (2 CTAs per SM by shared memory: keep 32 warps per SM)
 constexpr int K2J_UNROLL  = 4;                  // read words per lane and step (loads in flight)
 constexpr int K2J_PLOTS_PER_ITEM = 8;           // most plots one CTA streams past its table ...
 constexpr int K2J_WORDS_PER_ITEM = 24576;       // ... and about how many read words: items of similar length
@@ -117,14 +117,15 @@ constexpr int K2J_QCAP = 96;                    // per-warp queue of matched cel
 __device__ __forceinline__ uint32_t k2j_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t k2j_lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return (uint32_t)v; }
 
-__global__ void __launch_bounds__(K2J_THREADS, K2J_MINB)
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, (K2J_MINB * K2J_WARPS) / WARPS)
 k2_join_match(const K2JParams p)
 {
     extern __shared__ __align__(128) uint8_t s_blob[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ __align__(8) uint2 s_queue[K2J_WARPS][K2J_QCAP];
-    __shared__ uint32_t s_qn[K2J_WARPS];
-    __shared__ K2Strip s_strip[K2J_WARPS];
+    __shared__ __align__(8) uint2 s_queue[WARPS][K2J_QCAP];
+    __shared__ uint32_t s_qn[WARPS];
+    __shared__ K2Strip s_strip[WARPS];
     __shared__ unsigned long long s_eval;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -156,7 +157,7 @@ k2_join_match(const K2JParams p)
         const Plot pl = p.plots[pid];
         const int nblk = (pl.n + 32 * K2J_UNROLL - 1) / (32 * K2J_UNROLL);
         // blocks are dealt round-robin to the warps across the item's plots: warp w takes block b when (blk0 + b) % W == w
-        int b = (warp - blk0 % K2J_WARPS + K2J_WARPS) % K2J_WARPS;
+        int b = (warp - blk0 % WARPS + WARPS) % WARPS;
         blk0 += nblk;
         if (b >= nblk || pl.m <= 0) continue;            // warp-uniform
         const Operand opr = p.ops[pl.read_op];
@@ -170,7 +171,7 @@ k2_join_match(const K2JParams p)
         __syncwarp();
         const uint32_t* rw = p.hash + opr.hash_off;
         const int xoff = ch.pos0 - pl.miss;              // structure coordinate of table position 0 after the cut
-        for (; b < nblk; b += K2J_WARPS) {
+        for (; b < nblk; b += WARPS) {
             const int base = b * 32 * K2J_UNROLL + lane;
             uint32_t r[K2J_UNROLL];
             #pragma unroll
