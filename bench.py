@@ -387,7 +387,7 @@ def run_gpu_arm(args):
     def gather(r):
         """This rank's results to their input positions in the shared arrays (at N = 1 they are in input order already)."""
         if shared is not None:
-            multi.scatter_part(shared.results, my_tix, my_ids, r)
+            multi.scatter_part(shared.results, my_tix, my_ids, r, sv_task_off=sv_task_off)
 
     # ---- resident timing: upload once, K x run() ---------------------------------------------------
     eng.upload(batch)

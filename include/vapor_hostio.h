@@ -63,6 +63,13 @@ int vapor_io_chop_many(void* const* alns, int n_aln, int64_t n_win, const char* 
                        vapor_io_reads_t** result);
 int vapor_io_reads_free(vapor_io_reads_t* result);
 
+/* Input-order gather of sharded results ("results written into a pre-sized host array indexed by input
+ * position"): `src` holds n_runs runs of elements back to back, run r of run_len[r] elements goes to element run_dst[r]
+ * of `dst`.  One run = the tasks of one SV.  Replaces the `cat` of the per-contig outputs in the reference's workflow
+ * (wdl/VaPoRBedPerContig.wdl:102). */
+int vapor_host_scatter_runs(void* dst, const void* src, int64_t elem_bytes, const int64_t* run_dst, const int64_t* run_len,
+                            int64_t n_runs, int threads);
+
 /* cigar2alignstart_by_pos (Simple_function.pyx:309-337) on a SAM CIGAR string: out[0] = read offset, out[1] = miss_bp. */
 int vapor_io_cigar2alignstart(const char* cigar, int64_t align_start, int64_t start, int64_t* out);
 

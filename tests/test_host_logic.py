@@ -110,7 +110,15 @@ def _strong_worker(rank, world, port, tag, q):
     dist.barrier()
     if rank != 0:
         shared = multi.SharedResults(tag, int(sv_task_off[-1]), n_list, create=False)
-    multi.scatter_part(shared.results, multi.part_task_index(sv_task_off, mine), mine, _oracle_scorer(w.batch))
+    part = _oracle_scorer(w.batch)
+    multi.scatter_part(shared.results, multi.part_task_index(sv_task_off, mine), mine, part)                   # numpy route
+    check = _alloc_results(int(sv_task_off[-1]), n_list)
+    multi.scatter_part(check, None, mine, part, sv_task_off=sv_task_off)                                        # native route
+    tix = multi.part_task_index(sv_task_off, mine)
+    for f in part.__dataclass_fields__:
+        sel = tix if f.startswith("task_") else mine
+        assert np.array_equal(getattr(check, f)[sel], getattr(shared.results, f)[sel]), f
+    multi.scatter_part(shared.results, None, mine, part, sv_task_off=sv_task_off)
     dist.barrier()
     if rank == 0:
         q.put({f: np.array(getattr(shared.results, f)) for f in shared.results.__dataclass_fields__})

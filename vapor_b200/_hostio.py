@@ -21,7 +21,8 @@ class vapor_io_reads_t(C.Structure):
 
 
 EXPORTS = ["vapor_io_last_error", "vapor_io_fasta_open", "vapor_io_fasta_close", "vapor_io_fasta_fetch", "vapor_io_fasta_fetch_many",
-           "vapor_io_aln_open", "vapor_io_aln_close", "vapor_io_chop_many", "vapor_io_reads_free", "vapor_io_cigar2alignstart"]
+           "vapor_io_aln_open", "vapor_io_aln_close", "vapor_io_chop_many", "vapor_io_reads_free", "vapor_io_cigar2alignstart",
+           "vapor_host_scatter_runs"]
 _ready = False
 
 
@@ -41,6 +42,7 @@ def lib() -> C.CDLL:
         L.vapor_io_chop_many.argtypes = [C.POINTER(vp), i32, i64, C.c_char_p, vp, vp, vp, vp, i32, i32, C.POINTER(C.POINTER(vapor_io_reads_t))]
         L.vapor_io_reads_free.argtypes = [C.POINTER(vapor_io_reads_t)]
         L.vapor_io_cigar2alignstart.argtypes = [C.c_char_p, i64, i64, C.POINTER(i64)]
+        L.vapor_host_scatter_runs.argtypes = [vp, vp, i64, vp, vp, i64, i32]
         _ready = True
     return L
 
@@ -154,3 +156,12 @@ def cigar2alignstart(cigar: str, align_start: int, start: int) -> List[int]:
     out = (C.c_int64 * 2)()
     _check(lib().vapor_io_cigar2alignstart(cigar.encode("latin-1"), int(align_start), int(start), out), "vapor_io_cigar2alignstart")
     return [int(out[0]), int(out[1])]
+
+
+def scatter_runs(dst: np.ndarray, src: np.ndarray, run_dst: np.ndarray, run_len: np.ndarray, threads: int = 2) -> None:
+    """dst[run_dst[r] : run_dst[r] + run_len[r]] = the r-th run of ``src`` (runs back to back), rows of any width."""
+    assert dst.flags.c_contiguous and src.flags.c_contiguous and dst.dtype == src.dtype and dst.shape[1:] == src.shape[1:]
+    elem = dst.dtype.itemsize * int(np.prod(dst.shape[1:], dtype=np.int64))
+    rd = np.ascontiguousarray(run_dst, dtype=np.int64); rl = np.ascontiguousarray(run_len, dtype=np.int64)
+    _check(lib().vapor_host_scatter_runs(dst.ctypes.data, src.ctypes.data, elem, rd.ctypes.data, rl.ctypes.data, len(rd), threads),
+           "vapor_host_scatter_runs")

@@ -700,6 +700,20 @@ int vapor_io_reads_free(vapor_io_reads_t* result) {
     return VAPOR_OK;
 }
 
+int vapor_host_scatter_runs(void* dst, const void* src, int64_t elem_bytes, const int64_t* run_dst, const int64_t* run_len, int64_t n_runs, int threads) {
+    if (n_runs < 0 || elem_bytes <= 0 || (n_runs > 0 && (!dst || !src || !run_dst || !run_len))) return fail(VAPOR_E_ARG, "bad scatter arguments");
+    if (n_runs == 0) return VAPOR_OK;
+    std::vector<int64_t> src_off((size_t)n_runs + 1, 0);
+    for (int64_t r = 0; r < n_runs; ++r) { if (run_len[r] < 0 || run_dst[r] < 0) return fail(VAPOR_E_ARG, "negative run"); src_off[(size_t)r + 1] = src_off[(size_t)r] + run_len[r]; }
+    threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads > 0 ? threads : 2, n_runs / 4096 + 1));
+    uint8_t* d = static_cast<uint8_t*>(dst); const uint8_t* s_ = static_cast<const uint8_t*>(src);
+    run_threads(threads, [&](int t) {
+        for (int64_t r = n_runs * t / threads; r < n_runs * (t + 1) / threads; ++r)
+            memcpy(d + run_dst[r] * elem_bytes, s_ + src_off[(size_t)r] * elem_bytes, (size_t)(run_len[r] * elem_bytes));
+    });
+    return VAPOR_OK;
+}
+
 int vapor_io_cigar2alignstart(const char* cigar, int64_t align_start, int64_t start, int64_t* out) {
     if (!cigar || !out) return fail(VAPOR_E_ARG, "NULL argument");
     std::vector<uint32_t> ops;

@@ -194,14 +194,21 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
     __shared__ uint8_t s_lut[256];                               // the alphabet table, out of the constant cache:
                                                                  // a per-lane index there would replay 32 ways
     __shared__ __align__(16) uint8_t s_raw[K1_CHUNK + K1_MAXK + 24];
+    __shared__ int s_op;
     s_lut[threadIdx.x] = c_code_lut[threadIdx.x];
-    // locate (operand, chunk) of this CTA
-    int lo = 0, hi = n_ops;                 // last op with prefix <= blockIdx.x
+    // locate (operand, chunk) of this CTA: one thread searches, everybody reads the answer (the search is 17 dependent
+    // loads for a 100 000-operand wave -- a fifth of the kernel's instructions when all 256 threads repeat it)
     const int bid = blockIdx.x;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (chunk_prefix[mid] - chunk_base <= bid) lo = mid; else hi = mid;
+    if (threadIdx.x == 0) {
+        int lo_ = 0, hi_ = n_ops;                 // last op with prefix <= blockIdx.x
+        while (hi_ - lo_ > 1) {
+            const int mid = (lo_ + hi_) >> 1;
+            if (chunk_prefix[mid] - chunk_base <= bid) lo_ = mid; else hi_ = mid;
+        }
+        s_op = lo_;
     }
+    __syncthreads();
+    const int lo = s_op;
     const Operand op = ops[lo];
     const int chunk = bid - (chunk_prefix[lo] - chunk_base);
     const int base0 = chunk * K1_CHUNK;
@@ -209,7 +216,6 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
     const int nload = min(K1_CHUNK + k - 1, op.len - base0);     // bases this CTA needs
     const bool upper = (op.flags & OPF_UPPER) != 0;
     const uint8_t* src = seq + op.seq_begin + base0;
-    __syncthreads();
 
     // ---- bases -> codes: aligned 32-bit loads, four table look-ups, one 32-bit shared store ----------------
     const int head = (int)(reinterpret_cast<uintptr_t>(src) & 3);    // s_code[i] = code of base i lives at s_raw[head + i]

@@ -50,12 +50,22 @@ def part_task_index(sv_task_off: np.ndarray, sv_ids: np.ndarray) -> np.ndarray:
     return np.repeat(t0 - loc[:-1], cnt) + np.arange(loc[-1])
 
 
-def scatter_part(out: Results, tix: np.ndarray, sv_ids: np.ndarray, part: Results) -> None:
-    """Write one part's results to their input positions in ``out`` (pre-sized arrays of the whole list)."""
+def scatter_part(out: Results, tix: np.ndarray, sv_ids: np.ndarray, part: Results, sv_task_off: Optional[np.ndarray] = None) -> None:
+    """Write one part's results to their input positions in ``out`` (pre-sized arrays of the whole list).  With
+    ``sv_task_off`` (task offsets of the whole list) the copy is one native memcpy per SV (``vapor_host_scatter_runs``);
+    without it, numpy fancy indexing with the task positions ``tix``."""
     if len(sv_ids) == 0:
         return
-    for f in ("task_score", "task_status", "task_stat", "task_hits", "task_hitsum"):
-        getattr(out, f)[tix] = getattr(part, f)
+    sv_ids = np.asarray(sv_ids, dtype=np.int64)
+    if sv_task_off is not None:
+        from . import _hostio
+        run_dst = np.ascontiguousarray(sv_task_off[sv_ids], dtype=np.int64)
+        run_len = np.ascontiguousarray(sv_task_off[sv_ids + 1] - sv_task_off[sv_ids], dtype=np.int64)
+        for f in ("task_score", "task_status", "task_stat", "task_hits", "task_hitsum"):
+            _hostio.scatter_runs(getattr(out, f), np.ascontiguousarray(getattr(part, f)), run_dst, run_len)
+    else:
+        for f in ("task_score", "task_status", "task_stat", "task_hits", "task_hitsum"):
+            getattr(out, f)[tix] = getattr(part, f)
     for f in ("sv_qs", "sv_gs", "sv_gq", "sv_gt", "sv_nscore"):
         getattr(out, f)[sv_ids] = getattr(part, f)
 
@@ -65,7 +75,7 @@ def merge_results(batch: PackedBatch, parts: Sequence[np.ndarray], results: Sequ
     out = _alloc_results(batch.n_task, batch.n_sv)
     for sv_ids, r in zip(parts, results):
         if len(sv_ids):
-            scatter_part(out, part_task_index(batch.sv_task_off, sv_ids), np.asarray(sv_ids, dtype=np.int64), r)
+            scatter_part(out, None, np.asarray(sv_ids, dtype=np.int64), r, sv_task_off=batch.sv_task_off)
     return out
 
 
