@@ -363,6 +363,11 @@ def run_gpu_arm(args):
         opts["tile_variant"] = args.tile_variant
     if args.k2_mode >= 0:
         opts["k2_mode"] = args.k2_mode
+    if args.k3_mode >= 0:
+        opts["k3_mode"] = args.k3_mode
+    for kv in args.opt:
+        k_, v_ = kv.split("=")
+        opts[k_] = int(v_)
     if args.hit_budget_gb > 0:
         opts["hit_budget_bytes"] = int(args.hit_budget_gb * (1 << 30))
     if args.k2_ctas_per_sm > 0:
@@ -614,6 +619,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tile-variant", type=int, default=-1, help="tile-kernel inner loop (-1 = library default)")
     ap.add_argument("--k2-mode", type=int, default=-1, help="kernel 2: 1 = join (library default), 0 = all-pairs tile kernel")
+    ap.add_argument("--k3-mode", type=int, default=-1, help="kernel 3: 1 = warp per task (library default), 0 = CTA per task everywhere")
+    ap.add_argument("--opt", action="append", default=[], help="library tunable name=value (vapor_gpu_set_option), repeatable")
     ap.add_argument("--hit-budget-gb", type=float, default=0, help="device memory for the hit slab of one wave (0 = library default)")
     ap.add_argument("--k2-ctas-per-sm", type=int, default=0, help="persistent-grid size of the tile kernel (0 = occupancy)")
     args = ap.parse_args()

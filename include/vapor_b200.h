@@ -125,8 +125,11 @@ int vapor_gpu_set_hit_budget(void* handle, int64_t bytes);
  * the default -- only cells whose k-mer words share a bucket are compared; 0 = all-pairs tile kernel -- every cell
  * of every plot is compared; both emit the identical hit set); "tile_variant" (inner loop of the tile
  * kernel: 0 = 16 rows/lane by ISETP only, 1/2/3/4 = 14/16/12/13 rows by ISETP + 2 row polynomials of
- * 8 rows by IMAD; default 4), "k2_ctas_per_sm" (persistent-grid size of the tile kernel), "plan_threads" (host
- * threads used for planning, 0 = auto).  Takes effect at the next upload. */
+ * 8 rows by IMAD; default 4), "k2_ctas_per_sm" (persistent-grid size of the tile kernel), "k3_mode" (kernel 3:
+ * 1 = one warp per task for the small value ranges, the default; 0 = one CTA per task everywhere;
+ * "k3_warp_classes": how many of the scratch classes 2 048 / 4 096 / 8 192 / 16 384 / 26 624 bins go to the warp kernel,
+ * default 3), "overlap" (1 = kernel 3 of a wave runs on a second stream under kernels 1-2 of the next wave; default 0),
+ * "plan_threads" (host threads used for planning, 0 = auto).  Takes effect at the next upload. */
 int vapor_gpu_set_option(void* handle, const char* name, int64_t value);
 
 /* Blocking one-shot: host prep + H2D + kernels 1-4 + D2H.

@@ -50,6 +50,11 @@ def main():
             other = eng.score(w.batch)
             for f in res.__dataclass_fields__:
                 assert np.array_equal(getattr(res, f), getattr(other, f)), f"kernel-2 variants differ in {f}"
+        eng.set_option("k2_mode", 0 if a.k2_mode == 0 else 1)
+        eng.set_option("k3_mode", 0)                      # the CTA-per-task kernel 3 must agree with the warp-per-task one
+        other = eng.score(w.batch)
+        for f in res.__dataclass_fields__:
+            assert np.array_equal(getattr(res, f), getattr(other, f)), f"kernel-3 variants differ in {f}"
     t_gpu = time.time() - t0
     nt = w.batch.n_task
     step = max(1, nt // (a.procs * 8))

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libvapor_b200.so")
 SOURCES = ["api.cu", "hostio.cpp"]
-HEADERS = ["common.cuh", "k1_pack.cuh", "k2_tile.cuh", "k2_join.cuh", "k3_score.cuh", "k4_genotype.cuh",
+HEADERS = ["common.cuh", "k1_pack.cuh", "k2_tile.cuh", "k2_join.cuh", "k3_score.cuh", "k3_warp.cuh", "k4_genotype.cuh",
            os.path.join("..", "..", "include", "vapor_b200.h"), os.path.join("..", "..", "include", "vapor_hostio.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]

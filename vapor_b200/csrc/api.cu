@@ -9,6 +9,7 @@
 #include "k2_tile.cuh"
 #include "k2_join.cuh"
 #include "k3_score.cuh"
+#include "k3_warp.cuh"
 #include "k4_genotype.cuh"
 
 #include <algorithm>
@@ -63,8 +64,11 @@ struct Wave {
 };
 
 // kernel-3 scratch classes: bins that fit in shared memory, then a global-memory fallback
-constexpr int K3_NCLASS = 5;
-const int k3_class_cap[K3_NCLASS - 1] = {4096, 16384, 26624, 110000};
+// Classes 0 .. K3W_NCLASS-1 run on the warp-per-task kernel (k3_warp.cuh), the next one on the CTA-per-task kernel with
+// shared-memory scratch, the last one on the CTA kernel with global scratch.
+constexpr int K3_NCLASS = 7;
+constexpr int K3W_NCLASS = 5;
+const int k3_class_cap[K3_NCLASS - 1] = {2048, 4096, 8192, 16384, K3W_MAX_NB, 110000};
 
 // join-kernel launch classes by table blob size (dynamic shared memory of the launch)
 constexpr int K2J_NCLASS = 3;
@@ -82,6 +86,10 @@ struct Handle {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // kernel 3 of wave i runs here while kernels 1-2 of wave i+1 run on `stream`
+    int overlap = 0;                 // 1 = kernel 3 of wave i on stream2 under kernels 1-2 of wave i+1 (measured: -2.5 % of the step, but the
+                                     // phase times then overlap; off by default so that every kernel is timed alone)
+    std::vector<cudaEvent_t> ev_k2, ev_k3;       // per wave: kernel 2 done (stream), kernel 3 done (stream2)
     cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
     std::string err;
     int64_t hit_budget = 0;          // bytes; 0 = default
@@ -127,8 +135,10 @@ struct Handle {
     DevBuf<JoinItem> d_items;
     DevBuf<int32_t> d_chunk_prefix, d_op_status, d_class_ids, d_sv_nscore, d_jplots;
     DevBuf<int64_t> d_strip_prefix, d_sv_off;
-    DevBuf<uint32_t> d_hash, d_cnt, d_task_hits, d_gscratch, d_ovf_flags, d_qc;
-    DevBuf<uint2> d_hits, d_ovf_hits;
+    DevBuf<uint32_t> d_hash, d_cnt, d_task_hits, d_gscratch, d_ovf_flags, d_qc, d_k3q;
+    int k3_mode = 1;                 // 1 = warp-per-task kernel for the classes it covers, 0 = CTA-per-task kernel everywhere
+    int k3w_nclass = 3;              // classes 0 .. k3w_nclass-1 go to the warp kernel (measured: it wins up to 8 192 bins)
+    DevBuf<uint2> d_hits, d_hits2, d_ovf_hits;   // hit slabs of even / odd waves (d_hits2 only with overlap and > 1 wave)
     DevBuf<double> d_task_score, d_task_stat, d_pos, d_sv_qs, d_sv_gs, d_sv_gq;
     DevBuf<unsigned long long> d_task_hitsum, d_queue, d_stats;
     unsigned long long* h_stats = nullptr;       // pinned: [0] hits, [1] evaluated cells
@@ -143,18 +153,18 @@ struct Handle {
 
 enum { CAT_H2D = 0, CAT_PACK, CAT_TABLE, CAT_TILE, CAT_SCORE, CAT_GENO, CAT_D2H, CAT_N };
 
-int span_begin(Handle* h, int cat) {
+int span_begin(Handle* h, int cat, cudaStream_t st = nullptr) {
     if (h->ev_used == h->ev_pool.size()) {
         cudaEvent_t a, b;
         cudaEventCreate(&a); cudaEventCreate(&b);
         h->ev_pool.push_back({a, b});
     }
     size_t i = h->ev_used++;
-    cudaEventRecord(h->ev_pool[i].first, h->stream);
+    cudaEventRecord(h->ev_pool[i].first, st ? st : h->stream);
     h->spans.push_back({i, cat});
     return (int)i;
 }
-void span_end(Handle* h, int i) { cudaEventRecord(h->ev_pool[i].second, h->stream); }
+void span_end(Handle* h, int i, cudaStream_t st = nullptr) { cudaEventRecord(h->ev_pool[i].second, st ? st : h->stream); }
 
 void collect_spans(Handle* h, float* acc /*CAT_N*/) {
     for (auto& s : h->spans) {
@@ -730,12 +740,14 @@ int upload_impl(Handle* h, const vapor_batch_t* in) {
     CK(h->d_op_status.ensure(h->ops.size() + 1));
     CK(h->d_cnt.ensure(h->plots.size() + 1));
     CK(h->d_hits.ensure((size_t)h->max_wave_hits + 64));
+    if (h->overlap && h->waves.size() > 1) CK(h->d_hits2.ensure((size_t)h->max_wave_hits + 64));
     CK(h->d_task_score.ensure(nt + 1)); CK(h->d_task_status.ensure(nt + 1));
     CK(h->d_task_stat.ensure(4 * nt + 4)); CK(h->d_task_hits.ensure(4 * nt + 4)); CK(h->d_task_hitsum.ensure(4 * nt + 4));
     CK(h->d_pos.ensure(nt + 1));
     CK(h->d_sv_qs.ensure(nsv + 1)); CK(h->d_sv_gs.ensure(nsv + 1)); CK(h->d_sv_gq.ensure(nsv + 1));
     CK(h->d_sv_gt.ensure(nsv + 1)); CK(h->d_sv_nscore.ensure(nsv + 1));
     CK(h->d_queue.ensure(4)); CK(h->d_stats.ensure(4)); CK(h->d_ovf_flags.ensure(h->waves.size() + 1));
+    CK(h->d_k3q.ensure((h->waves.size() + 1) * K3_NCLASS));
     { int rcf = ensure_flags(h, h->waves.size() + 1); if (rcf) return rcf; }
     if (k3_class_of(h->max_nb) == K3_NCLASS - 1)
         CK(h->d_gscratch.ensure((size_t)2 * h->sm_count * k3_scratch_words(h->max_nb)));
@@ -815,15 +827,22 @@ int launch_k2_join(Handle* h, const JoinPlan& jp, size_t wi, K2JParams kp) {
 }
 
 // kernel 3 over task ids [o0, o1) of scratch class c
-void launch_k3_class(Handle* h, K3Params kp, int c, int max_nb) {
-    if (c < K3_NCLASS - 1) {
+// `slot` = this launch's task-queue counter in d_k3q (zeroed by the caller)
+void launch_k3_class(Handle* h, K3Params kp, int c, int max_nb, size_t slot, cudaStream_t st) {
+    if (c < h->k3w_nclass && h->k3_mode == 1) {
+        kp.nb_cap = k3_class_cap[c]; kp.use_global = 0; kp.gscratch = nullptr; kp.queue = h->d_k3q.p + slot;
+        const size_t smem = (size_t)K3W_TEAMS * k3w_scratch_words(kp.nb_cap) * sizeof(uint32_t);
+        const int per_sm = std::max(1, std::min(K3W_MINB, (int)((size_t)(226 * 1024) / (smem + 1024))));
+        const int grid = (int)std::min<int64_t>(((int64_t)kp.n_ids + K3W_TEAMS - 1) / K3W_TEAMS, (int64_t)h->sm_count * per_sm);
+        k3w_score_reads<<<grid, 32 * K3W_TEAMS, smem, st>>>(kp);
+    } else if (c < K3_NCLASS - 1) {
         kp.nb_cap = k3_class_cap[c]; kp.use_global = 0; kp.gscratch = nullptr;
         const size_t smem = k3_scratch_words(kp.nb_cap) * sizeof(uint32_t);
-        k3_score_reads<<<kp.n_ids, K3_THREADS, smem, h->stream>>>(kp);
+        k3_score_reads<<<kp.n_ids, K3_THREADS, smem, st>>>(kp);
     } else {
         kp.nb_cap = max_nb; kp.use_global = 1; kp.gscratch = h->d_gscratch.p;
         const int grid = std::min(kp.n_ids, 2 * h->sm_count);
-        k3_score_reads<<<grid, K3_THREADS, 0, h->stream>>>(kp);
+        k3_score_reads<<<grid, K3_THREADS, 0, st>>>(kp);
     }
 }
 
@@ -922,6 +941,7 @@ int redo_wave(Handle* h, size_t wi, int64_t* launches) {
     CKR(cudaMemcpyAsync(d_out.p, out_flat.data(), out_flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CKR(cudaMemsetAsync(d_recnt.p, 0, re_plots.size() * sizeof(uint32_t), h->stream));
     CKR(cudaMemsetAsync(d_reflag.p, 0, 4 * sizeof(uint32_t), h->stream));
+    CKR(cudaMemsetAsync(h->d_k3q.p + h->waves.size() * K3_NCLASS, 0, K3_NCLASS * sizeof(uint32_t), h->stream));
     if (h->waves.size() > 1) *launches += launch_k1_wave(h, w);      // later waves reused the word / code buffers
     CKR(cudaMemsetAsync(h->d_queue.p, 0, 4 * sizeof(unsigned long long), h->stream));
     int sp = span_begin(h, CAT_TILE);
@@ -943,7 +963,7 @@ int redo_wave(Handle* h, size_t wi, int64_t* launches) {
         kp.plots = d_re.p; kp.cnt = d_recnt.p; kp.op_status = h->d_op_status.p; kp.hits = h->d_ovf_hits.p;
         kp.task_score = h->d_task_score.p; kp.task_status = h->d_task_status.p; kp.task_stat = h->d_task_stat.p;
         kp.task_hits = h->d_task_hits.p; kp.task_hitsum = h->d_task_hitsum.p;
-        launch_k3_class(h, kp, c, std::max(re_max_nb, h->max_nb));
+        launch_k3_class(h, kp, c, std::max(re_max_nb, h->max_nb), h->waves.size() * K3_NCLASS + c, h->stream);
         ++*launches;
     }
     span_end(h, sp);
@@ -977,10 +997,25 @@ int run_impl(Handle* h) {
     CK(cudaMemsetAsync(h->d_cnt.p, 0, (h->plots.size() + 1) * sizeof(uint32_t), h->stream));
     CK(cudaMemsetAsync(h->d_ovf_flags.p, 0, (h->waves.size() + 1) * sizeof(uint32_t), h->stream));
     CK(cudaMemsetAsync(h->d_stats.p, 0, 4 * sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(h->d_k3q.p, 0, (h->waves.size() + 1) * K3_NCLASS * sizeof(uint32_t), h->stream));
 
+    // Kernel 3 of wave i runs on stream2 while kernels 1, 1b and 2 of wave i+1 run on stream: both sides are bound by
+    // latency and instruction issue at half occupancy, so together they fill the SMs better than one after the other.
+    // The hit slabs alternate between two buffers; kernel 2 of wave i waits for kernel 3 of wave i-2.
+    const bool ovl = h->overlap && !h->debug_sync && h->waves.size() > 1 && h->d_hits2.p != nullptr;
+    cudaStream_t s3 = ovl ? h->stream2 : h->stream;
+    if (ovl) {
+        while (h->ev_k2.size() < h->waves.size()) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            h->ev_k2.push_back(a); h->ev_k3.push_back(b);
+        }
+    }
     int sp;
     for (size_t wi = 0; wi < h->waves.size(); ++wi) {
         const Wave& w = h->waves[wi];
+        uint2* wave_hits = (ovl && (wi & 1)) ? h->d_hits2.p : h->d_hits.p;
+        if (ovl && wi >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_k3[wi - 2], 0));
         // ---- kernel 1 (+ 1b: tables of the structure-side operands) of this wave's operands ---------------
         sp = span_begin(h, CAT_PACK);
         launches += launch_k1_wave(h, w);
@@ -1011,7 +1046,7 @@ int run_impl(Handle* h) {
                 kp.n_strips = n_strips;
                 kp.strip_base = sbase;
                 kp.hash = h->d_hash.p; kp.code = h->d_code.p;
-                kp.hits = h->d_hits.p;
+                kp.hits = wave_hits;
                 kp.cnt = h->d_cnt.p + w.plot_begin;
                 kp.queue = h->d_queue.p;
                 kp.overflow = h->d_ovf_flags.p + wi;
@@ -1022,7 +1057,7 @@ int run_impl(Handle* h) {
             K2JParams kp{};
             kp.items = h->d_items.p; kp.jplots = h->d_jplots.p; kp.chunks = h->d_chunks.p; kp.plots = h->d_plots.p;
             kp.ops = h->d_ops.p; kp.hash = h->d_hash.p; kp.code = h->d_code.p; kp.table = h->d_table.p;
-            kp.hits = h->d_hits.p; kp.cnt = h->d_cnt.p; kp.overflow = h->d_ovf_flags.p + wi; kp.qc = nullptr;
+            kp.hits = wave_hits; kp.cnt = h->d_cnt.p; kp.overflow = h->d_ovf_flags.p + wi; kp.qc = nullptr;
             kp.evaluated = h->d_stats.p + 1;
             launches += launch_k2_join(h, h->jp, wi, kp);
         }
@@ -1030,22 +1065,29 @@ int run_impl(Handle* h) {
         CK(cudaGetLastError());
         CKL("kernel 2", 4);
         // ---- kernel 3, one launch per scratch class ----------------------------------------------
-        sp = span_begin(h, CAT_SCORE);
+        if (ovl) { CK(cudaEventRecord(h->ev_k2[wi], h->stream)); CK(cudaStreamWaitEvent(s3, h->ev_k2[wi], 0)); }
+        sp = span_begin(h, CAT_SCORE, s3);
         for (int c = 0; c < K3_NCLASS; ++c) {
             const int64_t o0 = h->class_off[wi * K3_NCLASS + c], o1 = h->class_off[wi * K3_NCLASS + c + 1];
             if (o1 == o0) continue;
             K3Params kp{};
             kp.tasks = h->d_tasks.p; kp.task_ids = h->d_class_ids.p + o0; kp.out_ids = nullptr; kp.n_ids = (int)(o1 - o0);
             kp.plots = h->d_plots.p; kp.cnt = h->d_cnt.p; kp.op_status = h->d_op_status.p;
-            kp.hits = h->d_hits.p;
+            kp.hits = wave_hits;
             kp.task_score = h->d_task_score.p; kp.task_status = h->d_task_status.p; kp.task_stat = h->d_task_stat.p;
             kp.task_hits = h->d_task_hits.p; kp.task_hitsum = h->d_task_hitsum.p;
-            launch_k3_class(h, kp, c, h->max_nb);
+            launch_k3_class(h, kp, c, h->max_nb, wi * K3_NCLASS + c, s3);
             ++launches;
             CKL("k3_score_reads", 8);
         }
-        span_end(h, sp);
+        span_end(h, sp, s3);
+        if (ovl) CK(cudaEventRecord(h->ev_k3[wi], s3));
         CK(cudaGetLastError());
+    }
+    if (ovl) {                                       // the summaries wait for the last two waves' scores
+        const size_t nw = h->waves.size();
+        CK(cudaStreamWaitEvent(h->stream, h->ev_k3[nw - 1], 0));
+        if (nw >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_k3[nw - 2], 0));
     }
     // ---- kernel 4 -------------------------------------------------------------------------
     auto genotype = [&]() -> int {
@@ -1296,12 +1338,15 @@ int vapor_gpu_open(int device, void** handle) {
             h->default_hit_budget = std::max<int64_t>((int64_t)1 << 30, std::min<int64_t>((int64_t)16 << 30, (int64_t)(free_b / 8)));
     }
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_open_error = cudaGetErrorString(e); delete h; return VAPOR_E_CUDA; }
     build_lut();
     e = cudaMemcpyToSymbol(c_code_lut, host_code_lut, 256);
     if (e != cudaSuccess) { g_open_error = std::string("kernel image not loadable on this device: ") + cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return VAPOR_E_CUDA; }
     e = cudaFuncSetAttribute(k3_score_reads, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(k3_scratch_words(k3_class_cap[K3_NCLASS - 2]) * sizeof(uint32_t)));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3w_score_reads, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(K3W_TEAMS * k3w_scratch_words(K3W_MAX_NB) * sizeof(uint32_t)));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_join_match<K2J_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2j_class_cap[K2J_NCLASS - 1]);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_join_match<K2J_WARPS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2j_class_cap[K2J_NCLASS - 1]);
     if (e != cudaSuccess) { g_open_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return VAPOR_E_CUDA; }
@@ -1318,12 +1363,16 @@ int vapor_gpu_close(void* handle) {
     Handle* h = static_cast<Handle*>(handle);
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->stream2) cudaStreamSynchronize(h->stream2);
     h->d_seq.release(); h->d_code.release(); h->d_task_status.release(); h->d_sv_gt.release(); h->d_table.release();
     h->d_ops.release(); h->d_plots.release(); h->d_tasks.release(); h->d_chunks.release(); h->d_items.release();
     h->d_chunk_prefix.release(); h->d_op_status.release(); h->d_class_ids.release(); h->d_sv_nscore.release(); h->d_jplots.release();
     h->d_strip_prefix.release(); h->d_sv_off.release();
-    h->d_hash.release(); h->d_cnt.release(); h->d_task_hits.release(); h->d_gscratch.release(); h->d_ovf_flags.release(); h->d_qc.release();
-    h->d_hits.release(); h->d_ovf_hits.release();
+    h->d_hash.release(); h->d_cnt.release(); h->d_task_hits.release(); h->d_gscratch.release(); h->d_ovf_flags.release(); h->d_qc.release(); h->d_k3q.release();
+    h->d_hits.release(); h->d_hits2.release(); h->d_ovf_hits.release();
+    for (cudaEvent_t e_ : h->ev_k2) cudaEventDestroy(e_);
+    for (cudaEvent_t e_ : h->ev_k3) cudaEventDestroy(e_);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     h->d_task_score.release(); h->d_task_stat.release(); h->d_pos.release(); h->d_sv_qs.release(); h->d_sv_gs.release(); h->d_sv_gq.release();
     h->d_task_hitsum.release(); h->d_queue.release(); h->d_stats.release();
     if (h->h_stats) cudaFreeHost(h->h_stats);
@@ -1356,6 +1405,19 @@ int vapor_gpu_set_option(void* handle, const char* name, int64_t value) {
         if (value < 0 || value > 1) { h->err = "k2_mode must be 0 (tile) or 1 (join)"; return VAPOR_E_ARG; }
         h->k2_mode = (int)value; h->resident = false; h->ran = false;             // the kernel-2 plan must be rebuilt
         return VAPOR_OK;
+    }
+    if (n == "k3_warp_classes") {
+        if (value < 0 || value > K3W_NCLASS) { h->err = "k3_warp_classes out of range"; return VAPOR_E_ARG; }
+        h->k3w_nclass = (int)value; return VAPOR_OK;
+    }
+    if (n == "overlap") {
+        if (value < 0 || value > 1) { h->err = "overlap must be 0 or 1"; return VAPOR_E_ARG; }
+        h->overlap = (int)value; h->resident = false; h->ran = false;             // the second hit slab is allocated at upload
+        return VAPOR_OK;
+    }
+    if (n == "k3_mode") {
+        if (value < 0 || value > 1) { h->err = "k3_mode must be 0 (CTA per task) or 1 (warp per task)"; return VAPOR_E_ARG; }
+        h->k3_mode = (int)value; return VAPOR_OK;
     }
     if (n == "plan_threads") {
         if (value < 0 || value > 256) { h->err = "plan_threads out of range"; return VAPOR_E_ARG; }

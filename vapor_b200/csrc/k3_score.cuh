@@ -532,6 +532,7 @@ struct K3Params {
     uint32_t* gscratch;          // global scratch, [gridDim.x][scratch_words] (only when smem is too small)
     int nb_cap;                  // bins the scratch can hold
     int use_global;
+    unsigned int* queue;         // warp kernel (k3_warp.cuh): next task of this launch
     double* task_score; uint8_t* task_status; double* task_stat; uint32_t* task_hits;
     unsigned long long* task_hitsum;
 };
