@@ -72,7 +72,7 @@ const int k3_class_cap[K3_NCLASS - 1] = {2048, 4096, 8192, 16384, K3W_MAX_NB, 11
 
 // join-kernel launch classes by table blob size (dynamic shared memory of the launch)
 constexpr int K2J_NCLASS = 3;
-const int k2j_class_cap[K2J_NCLASS] = {16640, k2j_blob_bytes(6144, k2j_bits(6144)), k2j_blob_bytes(K2J_CH, k2j_bits(K2J_CH))};
+const int k2j_class_cap[K2J_NCLASS] = {k2j_blob_bytes(2048, k2j_bits(2048)), k2j_blob_bytes(4096, k2j_bits(4096)), k2j_blob_bytes(K2J_CH, k2j_bits(K2J_CH))};
 
 // the k2 plan of a set of plots: strips for the tile kernel, or table chunks + items for the join kernel
 struct JoinPlan {

@@ -7,18 +7,25 @@
 // cells; this kernel looks only at cells whose canonical words share their top `bits` bits:
 //
 //   kernel 1b (k1b_build_tables): every structure-side operand chunk becomes a table -- its valid words
-//       counting-sorted by bucket key, the position of each sorted word, the bucket offsets (common.cuh, TabChunk);
+//       counting-sorted by bucket key, the position of each sorted word, the bucket offsets, and a membership bitmap
+//       over 4 more key bits than the buckets use (common.cuh, TabChunk);
 //   k2_join_match: one CTA stages one table in shared memory with ONE TMA bulk copy (cp.async.bulk + mbarrier)
-//       and streams the read words of every plot that uses the table past it, 128 read words per warp and step,
-//       straight from HBM/L2 in natural order (coalesced, four loads in flight per lane).  A lane looks its
-//       word's bucket up (two 16-bit offsets) and compares the word with the bucket's entries (1.3 on average), each
-//       lane on its own; a matched cell takes a slot of the per-warp queue with a shared-memory atomic, and the warp
-//       emits the queue with k2_flush of k2_tile.cuh (confirmation of hashed words, multiplicity of palindromes, QC
-//       counters, one global atomic per batch) -- the hit set is identical to the tile kernel's and to the
-//       reference's, only its order differs.
+//       and streams the read words of every plot that uses the table past it, straight from HBM/L2 in natural order
+//       (coalesced, four loads in flight per lane); every warp owns a contiguous share of the item's read words.
+//       Step 1, branch-free and converged: a lane tests its word against the membership bitmap (one shared-memory
+//       load).  77 % of the read words of a 15 %-error read match nothing, and 9 in 10 of those leave here.  The
+//       survivors are compacted (ballot + popc) into a per-warp list in shared memory.
+//       Step 2, whenever the list holds 32 survivors: one survivor per lane scans its bucket (two 16-bit offsets, 1-2
+//       entries on average) remembering up to two equal entries in registers -- no side effects inside the
+//       divergent loop -- and the warp parks the matched cells in its hit queue by ballot + popc (no atomics).
+//       Rounds are full warps by construction, the first version of this kernel ran its bucket scans with 17 of 32
+//       lanes active and spent 4.2 warp instructions per read word; this one spends about 1.
+//       The queue is emitted with k2_flush of k2_tile.cuh (confirmation of hashed words, multiplicity of
+//       palindromes, QC counters, one global atomic per batch) -- the hit set is identical to the tile kernel's and
+//       to the reference's, only its order differs.
 //
-// Cells evaluated = sum over read words of the size of their bucket (about n * (1 + m / 2^bits) per plot instead of
-// n * m); the kernel counts them (K2JParams::evaluated) so that throughput can be quoted on evaluated cells.
+// Cells evaluated = sum over the surviving read words of the size of their bucket; the kernel counts them
+// (K2JParams::evaluated) so that throughput can be quoted on evaluated cells.
 #pragma once
 #include "common.cuh"
 #include "k2_tile.cuh"
@@ -42,16 +49,23 @@ k1b_build_tables(const TabChunk* __restrict__ chunks, const Operand* __restrict_
                  const uint32_t* __restrict__ hash, uint8_t* __restrict__ table)
 {
     __shared__ uint32_t s_cnt[(1 << K2J_MAX_BITS) + 1];
+    __shared__ uint32_t s_bm[(1 << 16) / 32];                    // membership bitmap over the top fbits bits
     __shared__ uint32_t s_wtot[K1B_THREADS / 32];
     const TabChunk c = chunks[blockIdx.x];
     const int NB = 1 << c.bits;
+    const int fbits = k2j_fbits(c.bits), FW = (1 << fbits) / 32;
     const int tid = threadIdx.x;
     for (int q = tid; q <= NB; q += K1B_THREADS) s_cnt[q] = 0u;
+    for (int q = tid; q < FW; q += K1B_THREADS) s_bm[q] = 0u;
     __syncthreads();
     const uint32_t* w = hash + ops[c.op].hash_off + c.pos0;
     for (int i = tid; i < c.len; i += K1B_THREADS) {
         const uint32_t word = w[i];
-        if (word <= H_MAX_VALID) atomicAdd(&s_cnt[k2j_key(word, c.bits)], 1u);
+        if (word <= H_MAX_VALID) {
+            atomicAdd(&s_cnt[k2j_key(word, c.bits)], 1u);
+            const uint32_t fine = k2j_key(word, fbits), bit = 1u << (fine & 31u);
+            if (!(s_bm[fine >> 5] & bit)) atomicOr(&s_bm[fine >> 5], bit);
+        }
     }
     __syncthreads();
     // exclusive scan of s_cnt[0 .. NB): every thread owns NB / 256 consecutive counters (NB >= 256)
@@ -80,6 +94,8 @@ k1b_build_tables(const TabChunk* __restrict__ chunks, const Operand* __restrict_
     uint16_t* tp = reinterpret_cast<uint16_t*>(table + c.blob_off + 4 * (size_t)lp);
     uint16_t* toff = reinterpret_cast<uint16_t*>(table + c.blob_off + 6 * (size_t)lp);
     const uint32_t total = s_cnt[NB];
+    uint32_t* tbm = reinterpret_cast<uint32_t*>(table + c.blob_off + 6 * (size_t)lp + 2 * (size_t)(NB + 8));
+    for (int q = tid; q < FW; q += K1B_THREADS) tbm[q] = s_bm[q];
     for (int q = tid; q < NB + 8; q += K1B_THREADS) toff[q] = (uint16_t)(q <= NB ? s_cnt[q] : total);
     for (int i = (int)total + tid; i < lp; i += K1B_THREADS) { tw[i] = H_STRUCT_INVALID; tp[i] = 0; }   // defined padding
     __syncthreads();
@@ -113,6 +129,7 @@ struct K2JParams {
 #define K2J_MINB 4
 #endif
 constexpr int K2J_QCAP = 96;                    // per-warp queue of matched cells awaiting emission
+constexpr int K2J_LCAP = 96;                    // per-warp list of read words that passed the filter (< 32 carried + 64 new)
 
 __device__ __forceinline__ uint32_t k2j_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t k2j_lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return (uint32_t)v; }
@@ -124,11 +141,12 @@ k2_join_match(const K2JParams p)
     extern __shared__ __align__(128) uint8_t s_blob[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(8) uint2 s_queue[WARPS][K2J_QCAP];
-    __shared__ uint32_t s_qn[WARPS];
+    __shared__ __align__(8) uint2 s_list[WARPS][K2J_LCAP];
     __shared__ K2Strip s_strip[WARPS];
     __shared__ unsigned long long s_eval;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const JoinItem item = p.items[blockIdx.x];
     const TabChunk ch = p.chunks[item.chunk];
     if (threadIdx.x == 0) {
@@ -138,28 +156,82 @@ k2_join_match(const K2JParams p)
         mbar_expect_tx(&s_bar, (uint32_t)ch.blob_bytes);
         tma_bulk_g2s(s_blob, p.table + ch.blob_off, (uint32_t)ch.blob_bytes, &s_bar);
     }
-    if (lane == 0) s_qn[warp] = 0u;
     __syncthreads();                                     // the barrier is initialised before anyone waits on it
     const int lp = k2j_lp(ch.len);
     const uint32_t a_tw = smem_u32(s_blob);              // sorted words
     const uint32_t a_tp = a_tw + 4u * (uint32_t)lp;      // their positions
     const uint32_t a_off = a_tw + 6u * (uint32_t)lp;     // bucket offsets
-    const int shift = 30 - ch.bits;
+    const uint32_t a_bm = a_off + 2u * (uint32_t)((1 << ch.bits) + 8);   // membership bitmap
+    const int shift = 30 - ch.bits, fshift = 30 - k2j_fbits(ch.bits);
     uint2* queue = s_queue[warp];
-    uint32_t* qn = &s_qn[warp];
+    uint2* list = s_list[warp];
     K2Strip& st = s_strip[warp];
     uint32_t evaluated = 0;
+    int ln = 0, qn = 0;                                  // survivors listed, cells queued (warp-uniform)
     bool waited = false;
+    int xoff = 0;
 
-    int blk0 = 0;                                        // 128-word read blocks of the item's earlier plots
+    // One round: the last n_act listed survivors, one per lane, against their buckets.
+    auto round = [&](int n_act) {
+        __syncwarp();
+        const bool have = lane < n_act;
+        ln -= n_act;
+        const uint2 e = have ? list[ln + lane] : make_uint2(H_READ_PAD, 0u);
+        __syncwarp();                                    // everybody holds its survivor before the list is written again
+        const uint32_t word = e.x;
+        uint32_t idx = 0, end = 0;
+        if (have) {
+            const uint32_t ka = a_off + 2u * ((word & 0x3FFFFFFFu) >> shift);
+            idx = k2j_lds16(ka); end = k2j_lds16(ka + 2u);
+        }
+        evaluated += end - idx;
+        int m0 = -1, m1 = -1, m2 = -1;                   // first two equal entries; m2: where a third one sits (repeats)
+        for (; idx < end; ++idx) {
+            if (k2j_lds32(a_tw + 4u * idx) == word) {
+                if (m0 < 0) m0 = (int)idx; else if (m1 < 0) m1 = (int)idx; else { m2 = (int)idx; break; }
+            }
+        }
+        int x0 = -1, x1 = -1;
+        if (m0 >= 0) x0 = xoff + (int)k2j_lds16(a_tp + 2u * (uint32_t)m0);      // negative: before the cut, not a cell of the plot
+        if (m1 >= 0) x1 = xoff + (int)k2j_lds16(a_tp + 2u * (uint32_t)m1);
+        const unsigned b0 = __ballot_sync(0xFFFFFFFFu, x0 >= 0), b1 = __ballot_sync(0xFFFFFFFFu, x1 >= 0);
+        if (x0 >= 0) queue[qn + __popc(b0 & lt)] = make_uint2((uint32_t)x0 | (word & 0xC0000000u), e.y);
+        qn += __popc(b0);
+        if (x1 >= 0) queue[qn + __popc(b1 & lt)] = make_uint2((uint32_t)x1 | (word & 0xC0000000u), e.y);
+        qn += __popc(b1);
+        if (__any_sync(0xFFFFFFFFu, m2 >= 0)) {          // rare: a word that sits three or more times in its bucket
+            uint32_t i2 = m2 >= 0 ? (uint32_t)m2 : end;
+            while (true) {
+                int x = -1;
+                while (i2 < end && x < 0) {
+                    const uint32_t ii = i2++;
+                    if (k2j_lds32(a_tw + 4u * ii) == word) x = xoff + (int)k2j_lds16(a_tp + 2u * ii);
+                }
+                const unsigned bb = __ballot_sync(0xFFFFFFFFu, x >= 0);
+                if (bb == 0u) break;
+                if (qn + 32 > K2J_QCAP) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
+                if (x >= 0) queue[qn + __popc(bb & lt)] = make_uint2((uint32_t)x | (word & 0xC0000000u), e.y);
+                qn += __popc(bb);
+            }
+        }
+        if (qn > K2J_QCAP - 64) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
+    };
+
+    // every warp owns a contiguous share of the item's 128-word read blocks
+    int total = 0;
+    for (int jp = item.jp_begin; jp < item.jp_end; ++jp) {
+        const int n = p.plots[p.jplots[jp]].n;
+        total += (n + 32 * K2J_UNROLL - 1) / (32 * K2J_UNROLL);
+    }
+    const int w_lo = (int)(((long long)total * warp) / WARPS), w_hi = (int)(((long long)total * (warp + 1)) / WARPS);
+    int blk0 = 0;                                        // read blocks of the item's earlier plots
     for (int jp = item.jp_begin; jp < item.jp_end; ++jp) {
         const int pid = p.jplots[jp];
         const Plot pl = p.plots[pid];
         const int nblk = (pl.n + 32 * K2J_UNROLL - 1) / (32 * K2J_UNROLL);
-        // blocks are dealt round-robin to the warps across the item's plots: warp w takes block b when (blk0 + b) % W == w
-        int b = (warp - blk0 % WARPS + WARPS) % WARPS;
+        const int b_lo = max(w_lo - blk0, 0), b_hi = min(w_hi - blk0, nblk);
         blk0 += nblk;
-        if (b >= nblk || pl.m <= 0) continue;            // warp-uniform
+        if (b_lo >= b_hi || pl.m <= 0) continue;         // warp-uniform
         const Operand opr = p.ops[pl.read_op];
         __syncwarp();
         if (lane == 0) {
@@ -170,8 +242,8 @@ k2_join_match(const K2JParams p)
         }
         __syncwarp();
         const uint32_t* rw = p.hash + opr.hash_off;
-        const int xoff = ch.pos0 - pl.miss;              // structure coordinate of table position 0 after the cut
-        for (; b < nblk; b += WARPS) {
+        xoff = ch.pos0 - pl.miss;                        // structure coordinate of table position 0 after the cut
+        for (int b = b_lo; b < b_hi; ++b) {
             const int base = b * 32 * K2J_UNROLL + lane;
             uint32_t r[K2J_UNROLL];
             #pragma unroll
@@ -180,39 +252,16 @@ k2_join_match(const K2JParams p)
             #pragma unroll
             for (int u = 0; u < K2J_UNROLL; ++u) {
                 const uint32_t word = r[u];
-                uint32_t idx = 0, end = 0;
-                if (word <= H_MAX_VALID) {
-                    const uint32_t ka = a_off + 2u * ((word & 0x3FFFFFFFu) >> shift);
-                    idx = k2j_lds16(ka); end = k2j_lds16(ka + 2u);
-                }
-                evaluated += end - idx;
-                // every lane scans its own bucket; a matched cell takes a queue slot with a shared-memory atomic.  A lane that
-                // finds the queue full stops at that entry: the warp then empties the queue and the lane carries on.
-                while (true) {
-                    for (; idx < end; ++idx) {
-                        if (k2j_lds32(a_tw + 4u * idx) != word) continue;
-                        const int x = xoff + (int)k2j_lds16(a_tp + 2u * idx);
-                        if (x < 0) continue;
-                        const uint32_t slot = atomicAdd(qn, 1u);
-                        if (slot >= (uint32_t)K2J_QCAP) break;
-                        queue[slot] = make_uint2((uint32_t)x | (word & 0xC0000000u), (uint32_t)(base + 32 * u));
-                    }
-                    __syncwarp();                                    // every lane's slots and queue entries are visible
-                    const unsigned more = __ballot_sync(0xFFFFFFFFu, idx < end);
-                    const uint32_t have = min(*qn, (uint32_t)K2J_QCAP);
-                    if (more == 0u && have <= (uint32_t)(K2J_QCAP - 48)) break;
-                    __syncwarp();
-                    k2_flush(st, queue, (int)have, lane);
-                    __syncwarp();
-                    if (lane == 0) *qn = 0u;
-                    __syncwarp();
-                    if (more == 0u) break;
-                }
+                const uint32_t fine = (word & 0x3FFFFFFFu) >> fshift;
+                const bool pass = word <= H_MAX_VALID && ((k2j_lds32(a_bm + 4u * (fine >> 5)) >> (fine & 31u)) & 1u);
+                const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass);
+                if (pass) list[ln + __popc(pm & lt)] = make_uint2(word, (uint32_t)(base + 32 * u));
+                ln += __popc(pm);
+                if (u & 1) { while (ln >= 32) round(32); }
             }
         }
-        __syncwarp();
-        const uint32_t have = min(*qn, (uint32_t)K2J_QCAP);
-        if (have) { k2_flush(st, queue, (int)have, lane); __syncwarp(); if (lane == 0) *qn = 0u; }
+        if (ln > 0) round(ln);                           // the plot's last survivors (fewer than 32)
+        if (qn > 0) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; }
     }
     if (!waited) mbar_wait(&s_bar, 0);                   // nobody leaves while the bulk copy may still be landing
     unsigned long long ev = evaluated;
