@@ -133,7 +133,7 @@ struct Handle {
     DevBuf<Task> d_tasks;
     DevBuf<TabChunk> d_chunks;
     DevBuf<JoinItem> d_items;
-    DevBuf<int32_t> d_chunk_prefix, d_op_status, d_class_ids, d_sv_nscore, d_jplots;
+    DevBuf<int32_t> d_chunk_prefix, d_op_status, d_class_ids, d_sv_nscore, d_jplots, d_k1map;
     DevBuf<int64_t> d_strip_prefix, d_sv_off;
     DevBuf<uint32_t> d_hash, d_cnt, d_task_hits, d_gscratch, d_ovf_flags, d_qc, d_k3q;
     int k3_mode = 1;                 // 1 = warp-per-task kernel for the classes it covers, 0 = CTA-per-task kernel everywhere
@@ -733,6 +733,11 @@ int upload_impl(Handle* h, const vapor_batch_t* in) {
     CK(h->d_plots.ensure(h->plots.size() + 1));
     CK(h->d_tasks.ensure(nt + 1));
     CK(h->d_chunk_prefix.ensure(h->chunk_prefix.size()));
+    {
+        int64_t most = 0;                            // kernel-1 CTAs of the largest wave
+        for (const Wave& w : h->waves) most = std::max<int64_t>(most, h->chunk_prefix[w.op_end] - h->chunk_prefix[w.op_begin]);
+        CK(h->d_k1map.ensure((size_t)most + 1));
+    }
     CK(h->d_class_ids.ensure(nt + 1));
     CK(h->d_sv_off.ensure(nsv + 1));
     CK(h->d_hash.ensure((size_t)h->hash_elems));
@@ -851,10 +856,12 @@ int launch_k1_wave(Handle* h, const Wave& w) {
     const int n_ops = (int)(w.op_end - w.op_begin);
     if (n_ops <= 0) return 0;
     const int base = h->chunk_prefix[w.op_begin], n_chunks = h->chunk_prefix[w.op_end] - base;
+    if (n_chunks <= 0) return 0;
+    k1_map_chunks<<<(n_ops + 255) / 256, 256, 0, h->stream>>>(h->d_chunk_prefix.p + w.op_begin, base, n_ops, h->d_k1map.p);
     k1_pack_kmers<<<n_chunks, K1_THREADS, 0, h->stream>>>(
-        h->d_seq.p, h->d_ops.p + w.op_begin, h->d_chunk_prefix.p + w.op_begin, base, n_ops, h->d_hash.p, h->d_code.p,
+        h->d_seq.p, h->d_ops.p + w.op_begin, h->d_chunk_prefix.p + w.op_begin, h->d_k1map.p, base, n_ops, h->d_hash.p, h->d_code.p,
         h->d_op_status.p + w.op_begin);
-    return 1;
+    return 2;
 }
 
 __global__ void k_sum_counts(const uint32_t* __restrict__ cnt, long long n, unsigned long long* out) {
@@ -1366,7 +1373,7 @@ int vapor_gpu_close(void* handle) {
     if (h->stream2) cudaStreamSynchronize(h->stream2);
     h->d_seq.release(); h->d_code.release(); h->d_task_status.release(); h->d_sv_gt.release(); h->d_table.release();
     h->d_ops.release(); h->d_plots.release(); h->d_tasks.release(); h->d_chunks.release(); h->d_items.release();
-    h->d_chunk_prefix.release(); h->d_op_status.release(); h->d_class_ids.release(); h->d_sv_nscore.release(); h->d_jplots.release();
+    h->d_chunk_prefix.release(); h->d_op_status.release(); h->d_class_ids.release(); h->d_sv_nscore.release(); h->d_jplots.release(); h->d_k1map.release();
     h->d_strip_prefix.release(); h->d_sv_off.release();
     h->d_hash.release(); h->d_cnt.release(); h->d_task_hits.release(); h->d_gscratch.release(); h->d_ovf_flags.release(); h->d_qc.release(); h->d_k3q.release();
     h->d_hits.release(); h->d_hits2.release(); h->d_ovf_hits.release();
@@ -1573,8 +1580,12 @@ int vapor_gpu_selfplot_qc(void* handle, const uint8_t* seq_bytes, const int64_t*
     CK(cudaMemsetAsync(h->d_queue.p, 0, 4 * sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->d_ovf_flags.p, 0, 4 * sizeof(uint32_t), h->stream));
     CK(cudaMemsetAsync(h->d_stats.p, 0, 4 * sizeof(unsigned long long), h->stream));
-    k1_pack_kmers<<<chunk_prefix.back(), K1_THREADS, 0, h->stream>>>(
-        h->d_seq.p, h->d_ops.p, h->d_chunk_prefix.p, 0, (int)ns, h->d_hash.p, h->d_code.p, h->d_op_status.p);
+    CK(h->d_k1map.ensure((size_t)chunk_prefix.back() + 1));
+    if (chunk_prefix.back() > 0) {
+        k1_map_chunks<<<(unsigned)((ns + 255) / 256), 256, 0, h->stream>>>(h->d_chunk_prefix.p, 0, (int)ns, h->d_k1map.p);
+        k1_pack_kmers<<<chunk_prefix.back(), K1_THREADS, 0, h->stream>>>(
+            h->d_seq.p, h->d_ops.p, h->d_chunk_prefix.p, h->d_k1map.p, 0, (int)ns, h->d_hash.p, h->d_code.p, h->d_op_status.p);
+    }
     CK(cudaGetLastError());
     if (mode == 0) {
         if (strip_prefix.back() > 0) {

@@ -63,8 +63,9 @@ struct Task {              // one read of one SV/allele
 // ---- join variant of kernel 2 (k2_join.cuh) -----------------------------------------------------
 // A structure-side operand is cut into chunks of at most K2J_CH k-mer positions; kernel 1b turns every chunk into a
 // *table*: its valid words counting-sorted by the top `bits` bits of the 30-bit payload, the position of every
-// sorted word, the 2^bits + 1 bucket offsets, and a membership bitmap over the top `fbits` = min(bits + 4, 16) bits
-// (the pre-filter: three quarters of the read words match nothing and leave after one shared-memory load).
+// sorted word, the 2^bits + 1 bucket offsets, and a membership bitmap over the top `fbits` bits (2^fbits >= 8 len, 12..16:
+// at most one bit in eight is set) -- the pre-filter: three quarters of the read words match nothing and leave after one
+// shared-memory load.
 // One blob per chunk, staged into shared memory by one TMA bulk copy:
 //   uint32 word[Lp] | uint16 pos[Lp] | uint16 off[2^bits + 8] | uint32 filter[2^fbits / 32]      Lp = len rounded up to 8
 constexpr int K2J_CH       = 8192;             // positions per table chunk (pos fits 16 bits; blob <= 66 KB)
@@ -89,9 +90,13 @@ __host__ __device__ inline int k2j_bits(int len) {
     while (b < K2J_MAX_BITS && (1 << b) < len) ++b;
     return b;
 }
-__host__ __device__ inline int k2j_fbits(int bits) { return bits + 4 < 16 ? bits + 4 : 16; }
+__host__ __device__ inline int k2j_fbits(int len) {
+    int f = 12;
+    while (f < 16 && (1 << f) < 8 * len) ++f;
+    return f;
+}
 __host__ __device__ inline int k2j_blob_bytes(int len, int bits) {
-    return 6 * k2j_lp(len) + 2 * ((1 << bits) + 8) + (1 << k2j_fbits(bits)) / 8;
+    return 6 * k2j_lp(len) + 2 * ((1 << bits) + 8) + (1 << k2j_fbits(len)) / 8;
 }
 
 struct JoinItem {          // one CTA of the join kernel: one table chunk against a few plots that use it

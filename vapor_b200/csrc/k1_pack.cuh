@@ -14,10 +14,11 @@
 //              bit 31 is set and the word is a symmetric hash of (forward, revcomp) that the
 //              tile kernel confirms on the code strings.  Bit 30 marks a k-mer that is its own
 //              reverse complement: the reference appends such a read position twice.
-// HBM-bound: 1 B/base read, 1 B/base + 4 B/position written.  Bases are read with aligned 32-bit loads and turned
-// into codes through a shared-memory copy of the alphabet table; every thread then owns 8 consecutive positions and
-// *rolls* the 2-bit forward / reverse-complement words of its window from one position to the next (k <= 15), so the
-// work per position is O(1), not O(k); results leave as 16-byte (words) and 8-byte (codes) stores.
+// 1 B/base read, 1 B/base + 4 B/position written.  Bases are read with aligned 32-bit loads and turned into codes
+// through a shared-memory copy of the alphabet table, then (k <= 15) packed 2 bits per base; every thread owns 8
+// consecutive positions and cuts each window's word out of two packed words with one funnel shift (k1_run_exact) --
+// O(1) per position with no state carried between positions; k > 15 rolls two polynomial hashes instead (k1_run).
+// Results leave as 16-byte (words) and 8-byte (codes) stores.
 #pragma once
 #include "common.cuh"
 
@@ -181,34 +182,103 @@ __device__ __forceinline__ bool k1_run(const uint8_t* s_code, const Operand& op,
 }
 
 
+// Words and codes of one thread's run of K1_RUN positions for k <= 15, from the chunk's 2-bit packed bases (16 per word,
+// base i at bits 2i) and its "not plain ACGT" / "invalid" bit strings (32 per word).  With g = the window's bases packed
+// first-base-lowest, the reverse-complement word of the rolling form (r = sum (3 - c_t) << 2t) is ~g, and the forward word
+// (f = sum c_t << 2(k-1-t)) is g with its k base pairs in reverse order: brev + a swap inside the pairs.  No per-thread
+// window set-up, no state carried from one position to the next: 30 instructions per position instead of 128.
+__device__ __forceinline__ bool k1_run_exact(const uint8_t* s_code, const uint32_t* s_p2, const uint32_t* s_np, const uint32_t* s_inv,
+                                             const Operand& op, int base0, int k,
+                                             uint32_t* __restrict__ hash, uint8_t* __restrict__ code)
+{
+    const int npos_code = min(K1_CHUNK, op.len - base0);          // bases owned by this chunk
+    const int npos_hash = min(K1_CHUNK, op.n - base0);            // k-mers owned by this chunk (may be <= 0)
+    const bool is_read = (op.flags & OPF_READ) != 0;
+    bool bad_read = false;
+    const int p0 = threadIdx.x * K1_RUN;
+    if (p0 < npos_code) {
+        const uint32_t mask = (1u << (2 * k)) - 1u, kmask = (1u << k) - 1u;
+        const int wi = p0 >> 4, off = (2 * p0) & 31, bi = p0 >> 5, boff = p0 & 31;
+        const uint32_t w0 = s_p2[wi], w1 = s_p2[wi + 1];
+        const uint32_t n0 = s_np[bi], n1 = s_np[bi + 1], v0 = s_inv[bi], v1 = s_inv[bi + 1];
+        const int rsh = 32 - 2 * k;
+        uint32_t* hp = hash + op.hash_off + base0 + p0;
+        uint8_t* cp = code + op.code_off + base0 + p0;
+        #pragma unroll
+        for (int half = 0; half < K1_RUN / 4; ++half) {             // four positions at a time: one 16-byte and one 4-byte store
+            uint32_t words[4];
+            uint32_t codes = 0;
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = 4 * half + j, p = p0 + i;
+                const uint32_t c0 = (p < npos_code) ? s_code[p] : 0u;
+                uint32_t h = H_STRUCT_INVALID;
+                bool pal = false;
+                if (p < npos_hash) {
+                    if ((__funnelshift_r(n0, n1, boff + i) & kmask) == 0u) {
+                        const uint32_t g = __funnelshift_r(w0, w1, off + 2 * i) & mask;
+                        const uint32_t r = ~g & mask;
+                        const uint32_t b = __brev(g);
+                        const uint32_t f = (((b & 0x55555555u) << 1) | ((b >> 1) & 0x55555555u)) >> rsh;
+                        pal = (f == r);
+                        h = mix30(min(f, r)) | (pal ? H_PALINDROME : 0u);
+                    } else if ((__funnelshift_r(v0, v1, boff + i) & kmask) != 0u) {
+                        if (is_read) { bad_read = true; h = H_READ_PAD; }
+                    } else {
+                        h = k1_hashed_word(s_code + p, k, pal);
+                    }
+                }
+                words[j] = h;
+                codes |= (c0 | (pal ? 0x80u : 0u)) << (8 * j);
+            }
+            const int q0 = p0 + 4 * half;
+            if (q0 + 4 <= npos_hash) {
+                reinterpret_cast<uint4*>(hp)[half] = make_uint4(words[0], words[1], words[2], words[3]);
+            } else {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) if (q0 + j < npos_hash) hp[4 * half + j] = words[j];
+            }
+            if (q0 + 4 <= npos_code) {
+                reinterpret_cast<uint32_t*>(cp)[half] = codes;
+            } else {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) if (q0 + j < npos_code) cp[4 * half + j] = (uint8_t)(codes >> (8 * j));
+            }
+        }
+    }
+    return bad_read;
+}
+
 #ifndef K1_MINB
 #define K1_MINB 8                              // measured: 8 resident CTAs per SM (32 registers)
 #endif
 
+// operand of every CTA of a k1_pack_kmers launch (one thread per operand): the kernel used to find it by a 17-step binary
+// search over the chunk prefix -- dependent global loads that were 39 % of its stall samples
+__global__ void k1_map_chunks(const int32_t* __restrict__ chunk_prefix, int chunk_base, int n_ops, int32_t* __restrict__ cta_op) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_ops) return;
+    for (int c = chunk_prefix[o] - chunk_base, e = chunk_prefix[o + 1] - chunk_base; c < e; ++c) cta_op[c] = o;
+}
+
+constexpr int K1_PACK_GROUPS = (K1_CHUNK + 64) / 8;              // 8-base groups packed per chunk (the chunk + the longest window + slack)
+
 __global__ void __launch_bounds__(K1_THREADS, K1_MINB)
 k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
               const int32_t* __restrict__ chunk_prefix,   // [n_ops+1] cumulative chunk counts, offset by chunk_base
+              const int32_t* __restrict__ cta_op,         // operand of every CTA (k1_map_chunks)
               int chunk_base, int n_ops, uint32_t* __restrict__ hash, uint8_t* __restrict__ code,
               int32_t* __restrict__ op_status)
 {
     __shared__ uint8_t s_lut[256];                               // the alphabet table, out of the constant cache:
                                                                  // a per-lane index there would replay 32 ways
     __shared__ __align__(16) uint8_t s_raw[K1_CHUNK + K1_MAXK + 24];
-    __shared__ int s_op;
+    __shared__ __align__(4) uint16_t s_p2[K1_PACK_GROUPS + 2];   // 2-bit codes, 8 bases per entry (k <= 15)
+    __shared__ __align__(4) uint8_t s_np[K1_PACK_GROUPS + 8];    // "not plain ACGT" bits, 8 bases per entry
+    __shared__ __align__(4) uint8_t s_inv[K1_PACK_GROUPS + 8];   // "invalid character" bits
     s_lut[threadIdx.x] = c_code_lut[threadIdx.x];
-    // locate (operand, chunk) of this CTA: one thread searches, everybody reads the answer (the search is 17 dependent
-    // loads for a 100 000-operand wave -- a fifth of the kernel's instructions when all 256 threads repeat it)
     const int bid = blockIdx.x;
-    if (threadIdx.x == 0) {
-        int lo_ = 0, hi_ = n_ops;                 // last op with prefix <= blockIdx.x
-        while (hi_ - lo_ > 1) {
-            const int mid = (lo_ + hi_) >> 1;
-            if (chunk_prefix[mid] - chunk_base <= bid) lo_ = mid; else hi_ = mid;
-        }
-        s_op = lo_;
-    }
-    __syncthreads();
-    const int lo = s_op;
+    const int lo = cta_op[bid];
     const Operand op = ops[lo];
     const int chunk = bid - (chunk_prefix[lo] - chunk_base);
     const int base0 = chunk * K1_CHUNK;
@@ -219,6 +289,7 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
 
     // ---- bases -> codes: aligned 32-bit loads, four table look-ups, one 32-bit shared store ----------------
     const int head = (int)(reinterpret_cast<uintptr_t>(src) & 3);    // s_code[i] = code of base i lives at s_raw[head + i]
+    __syncthreads();                                                 // s_lut is complete
     {
         const uint32_t* src4 = reinterpret_cast<const uint32_t*>(src - head);
         const int nwords = (head + nload + 3) >> 2;
@@ -236,7 +307,27 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
     __syncthreads();
     const uint8_t* s_code = s_raw + head;
 
-    const bool bad_read = (k <= 15) ? k1_run<true>(s_code, op, base0, k, hash, code) : k1_run<false>(s_code, op, base0, k, hash, code);
+    bool bad_read;
+    if (k <= 15) {
+        // pack the chunk: 2 bits per base + the two flag bits per base, 8 bases per thread and step
+        for (int g8 = threadIdx.x; g8 < K1_PACK_GROUPS; g8 += K1_THREADS) {
+            uint32_t p2 = 0, np = 0, iv = 0;
+            #pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int i = 8 * g8 + e;
+                const uint32_t c = i < nload ? s_code[i] : 0u;
+                p2 |= (c & 3u) << (2 * e);
+                np |= (uint32_t)(c >= 4u) << e;
+                iv |= (uint32_t)(c == (uint32_t)CODE_INVALID) << e;
+            }
+            s_p2[g8] = (uint16_t)p2; s_np[g8] = (uint8_t)np; s_inv[g8] = (uint8_t)iv;
+        }
+        __syncthreads();
+        bad_read = k1_run_exact(s_code, reinterpret_cast<const uint32_t*>(s_p2), reinterpret_cast<const uint32_t*>(s_np),
+                                reinterpret_cast<const uint32_t*>(s_inv), op, base0, k, hash, code);
+    } else {
+        bad_read = k1_run<false>(s_code, op, base0, k, hash, code);
+    }
     if (bad_read) atomicOr(&op_status[lo], 1);
 }
 

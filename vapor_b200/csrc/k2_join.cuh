@@ -36,8 +36,14 @@ constexpr int K1B_THREADS = 256;
 constexpr int K2J_WARPS     = 8;                // warps per CTA (tables up to 44 KB: 4 CTAs per SM)
 constexpr int K2J_WARPS_BIG = 16;               // ... for the largest tables (2 CTAs per SM by shared memory: keep 32 warps per SM)
 constexpr int K2J_UNROLL  = 4;                  // read words per lane and step (loads in flight)
-constexpr int K2J_PLOTS_PER_ITEM = 8;           // most plots one CTA streams past its table ...
-constexpr int K2J_WORDS_PER_ITEM = 24576;       // ... and about how many read words: items of similar length
+#ifndef K2J_PLOTS_N
+#define K2J_PLOTS_N 24
+#endif
+#ifndef K2J_WORDS_N
+#define K2J_WORDS_N 65536
+#endif
+constexpr int K2J_PLOTS_PER_ITEM = K2J_PLOTS_N;      // most plots one CTA streams past its table ...
+constexpr int K2J_WORDS_PER_ITEM = K2J_WORDS_N;      // ... and about how many read words: items of similar length
 
 __host__ __device__ __forceinline__ uint32_t k2j_key(uint32_t word, int bits) {
     return (word & 0x3FFFFFFFu) >> (30 - bits);
@@ -53,7 +59,7 @@ k1b_build_tables(const TabChunk* __restrict__ chunks, const Operand* __restrict_
     __shared__ uint32_t s_wtot[K1B_THREADS / 32];
     const TabChunk c = chunks[blockIdx.x];
     const int NB = 1 << c.bits;
-    const int fbits = k2j_fbits(c.bits), FW = (1 << fbits) / 32;
+    const int fbits = k2j_fbits(c.len), FW = (1 << fbits) / 32;
     const int tid = threadIdx.x;
     for (int q = tid; q <= NB; q += K1B_THREADS) s_cnt[q] = 0u;
     for (int q = tid; q < FW; q += K1B_THREADS) s_bm[q] = 0u;
@@ -129,10 +135,16 @@ struct K2JParams {
 #define K2J_MINB 4
 #endif
 constexpr int K2J_QCAP = 96;                    // per-warp queue of matched cells awaiting emission
-constexpr int K2J_LCAP = 96;                    // per-warp list of read words that passed the filter (< 32 carried + 64 new)
+constexpr int K2J_LCAP = 160;                   // per-warp list of read words that passed the filter (< 32 carried + 128 new)
 
 __device__ __forceinline__ uint32_t k2j_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t k2j_lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return (uint32_t)v; }
+
+struct K2JPlot {            // what the warps need to know about one plot of the item (shared memory, filled once per CTA)
+    K2Strip st;
+    const uint32_t* rw;     // the read's k-mer words
+    int n, m, xoff, nblk;   // read k-mers, structure k-mers after the cut, structure coordinate of table position 0, 128-word blocks
+};
 
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, (K2J_MINB * K2J_WARPS) / WARPS)
@@ -142,7 +154,7 @@ k2_join_match(const K2JParams p)
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(8) uint2 s_queue[WARPS][K2J_QCAP];
     __shared__ __align__(8) uint2 s_list[WARPS][K2J_LCAP];
-    __shared__ K2Strip s_strip[WARPS];
+    __shared__ __align__(8) K2JPlot s_plot[K2J_PLOTS_PER_ITEM];
     __shared__ unsigned long long s_eval;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -156,99 +168,62 @@ k2_join_match(const K2JParams p)
         mbar_expect_tx(&s_bar, (uint32_t)ch.blob_bytes);
         tma_bulk_g2s(s_blob, p.table + ch.blob_off, (uint32_t)ch.blob_bytes, &s_bar);
     }
-    __syncthreads();                                     // the barrier is initialised before anyone waits on it
+    // the item's plots, one thread each: three dependent global loads per plot happen here, once and in parallel, instead of
+    // in front of every warp's visit of the plot
+    const int n_plots = item.jp_end - item.jp_begin;
+    if ((int)threadIdx.x < n_plots) {
+        const int pid = p.jplots[item.jp_begin + threadIdx.x];
+        const Plot pl = p.plots[pid];
+        const Operand opr = p.ops[pl.read_op];
+        const Operand ops_ = p.ops[pl.struct_op];
+        K2JPlot& q = s_plot[threadIdx.x];
+        q.st.code_read = p.code + opr.code_off; q.st.code_struct = p.code + ops_.code_off + pl.miss;
+        q.st.cnt = p.cnt + pid; q.st.hits = p.hits + pl.hit_off; q.st.overflow = p.overflow; q.st.cap = pl.cap; q.st.k = opr.k; q.st.swap = false;
+        q.st.qc = (pl.kind & PLOT_QC) ? p.qc + pl.hit_off * QC_WORDS : nullptr;
+        q.rw = p.hash + opr.hash_off;
+        q.n = pl.n; q.m = pl.m; q.xoff = ch.pos0 - pl.miss;
+        q.nblk = pl.m > 0 ? (pl.n + 32 * K2J_UNROLL - 1) / (32 * K2J_UNROLL) : 0;
+    }
+    __syncthreads();                                     // the barrier is initialised before anyone waits on it; s_plot is filled
     const int lp = k2j_lp(ch.len);
     const uint32_t a_tw = smem_u32(s_blob);              // sorted words
     const uint32_t a_tp = a_tw + 4u * (uint32_t)lp;      // their positions
     const uint32_t a_off = a_tw + 6u * (uint32_t)lp;     // bucket offsets
     const uint32_t a_bm = a_off + 2u * (uint32_t)((1 << ch.bits) + 8);   // membership bitmap
-    const int shift = 30 - ch.bits, fshift = 30 - k2j_fbits(ch.bits);
+    const int shift = 30 - ch.bits, fshift = 30 - k2j_fbits(ch.len);
     uint2* queue = s_queue[warp];
     uint2* list = s_list[warp];
-    K2Strip& st = s_strip[warp];
     uint32_t evaluated = 0;
     int ln = 0, qn = 0;                                  // survivors listed, cells queued (warp-uniform)
     bool waited = false;
-    int xoff = 0;
-
-    // One round: the last n_act listed survivors, one per lane, against their buckets.
-    auto round = [&](int n_act) {
-        __syncwarp();
-        const bool have = lane < n_act;
-        ln -= n_act;
-        const uint2 e = have ? list[ln + lane] : make_uint2(H_READ_PAD, 0u);
-        __syncwarp();                                    // everybody holds its survivor before the list is written again
-        const uint32_t word = e.x;
-        uint32_t idx = 0, end = 0;
-        if (have) {
-            const uint32_t ka = a_off + 2u * ((word & 0x3FFFFFFFu) >> shift);
-            idx = k2j_lds16(ka); end = k2j_lds16(ka + 2u);
-        }
-        evaluated += end - idx;
-        int m0 = -1, m1 = -1, m2 = -1;                   // first two equal entries; m2: where a third one sits (repeats)
-        for (; idx < end; ++idx) {
-            if (k2j_lds32(a_tw + 4u * idx) == word) {
-                if (m0 < 0) m0 = (int)idx; else if (m1 < 0) m1 = (int)idx; else { m2 = (int)idx; break; }
-            }
-        }
-        int x0 = -1, x1 = -1;
-        if (m0 >= 0) x0 = xoff + (int)k2j_lds16(a_tp + 2u * (uint32_t)m0);      // negative: before the cut, not a cell of the plot
-        if (m1 >= 0) x1 = xoff + (int)k2j_lds16(a_tp + 2u * (uint32_t)m1);
-        const unsigned b0 = __ballot_sync(0xFFFFFFFFu, x0 >= 0), b1 = __ballot_sync(0xFFFFFFFFu, x1 >= 0);
-        if (x0 >= 0) queue[qn + __popc(b0 & lt)] = make_uint2((uint32_t)x0 | (word & 0xC0000000u), e.y);
-        qn += __popc(b0);
-        if (x1 >= 0) queue[qn + __popc(b1 & lt)] = make_uint2((uint32_t)x1 | (word & 0xC0000000u), e.y);
-        qn += __popc(b1);
-        if (__any_sync(0xFFFFFFFFu, m2 >= 0)) {          // rare: a word that sits three or more times in its bucket
-            uint32_t i2 = m2 >= 0 ? (uint32_t)m2 : end;
-            while (true) {
-                int x = -1;
-                while (i2 < end && x < 0) {
-                    const uint32_t ii = i2++;
-                    if (k2j_lds32(a_tw + 4u * ii) == word) x = xoff + (int)k2j_lds16(a_tp + 2u * ii);
-                }
-                const unsigned bb = __ballot_sync(0xFFFFFFFFu, x >= 0);
-                if (bb == 0u) break;
-                if (qn + 32 > K2J_QCAP) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
-                if (x >= 0) queue[qn + __popc(bb & lt)] = make_uint2((uint32_t)x | (word & 0xC0000000u), e.y);
-                qn += __popc(bb);
-            }
-        }
-        if (qn > K2J_QCAP - 64) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
-    };
 
     // every warp owns a contiguous share of the item's 128-word read blocks
     int total = 0;
-    for (int jp = item.jp_begin; jp < item.jp_end; ++jp) {
-        const int n = p.plots[p.jplots[jp]].n;
-        total += (n + 32 * K2J_UNROLL - 1) / (32 * K2J_UNROLL);
-    }
+    for (int j = 0; j < n_plots; ++j) total += s_plot[j].nblk;
     const int w_lo = (int)(((long long)total * warp) / WARPS), w_hi = (int)(((long long)total * (warp + 1)) / WARPS);
     int blk0 = 0;                                        // read blocks of the item's earlier plots
-    for (int jp = item.jp_begin; jp < item.jp_end; ++jp) {
-        const int pid = p.jplots[jp];
-        const Plot pl = p.plots[pid];
-        const int nblk = (pl.n + 32 * K2J_UNROLL - 1) / (32 * K2J_UNROLL);
+    for (int j = 0; j < n_plots; ++j) {
+        const K2JPlot& pq = s_plot[j];
+        const int nblk = pq.nblk;
         const int b_lo = max(w_lo - blk0, 0), b_hi = min(w_hi - blk0, nblk);
         blk0 += nblk;
-        if (b_lo >= b_hi || pl.m <= 0) continue;         // warp-uniform
-        const Operand opr = p.ops[pl.read_op];
-        __syncwarp();
-        if (lane == 0) {
-            const Operand ops_ = p.ops[pl.struct_op];
-            st.code_read = p.code + opr.code_off; st.code_struct = p.code + ops_.code_off + pl.miss;
-            st.cnt = p.cnt + pid; st.hits = p.hits + pl.hit_off; st.overflow = p.overflow; st.cap = pl.cap; st.k = opr.k; st.swap = false;
-            st.qc = (pl.kind & PLOT_QC) ? p.qc + pl.hit_off * QC_WORDS : nullptr;
-        }
-        __syncwarp();
-        const uint32_t* rw = p.hash + opr.hash_off;
-        xoff = ch.pos0 - pl.miss;                        // structure coordinate of table position 0 after the cut
+        if (b_lo >= b_hi) continue;                      // warp-uniform
+        const K2Strip& st = pq.st;
+        const uint32_t* rw = pq.rw;
+        const int n = pq.n, xoff = pq.xoff;
+        uint32_t r[K2J_UNROLL], rn[K2J_UNROLL];          // this block's words, the next block's (in flight while this one is probed)
+        #pragma unroll
+        for (int u = 0; u < K2J_UNROLL; ++u) { const int i = b_lo * 32 * K2J_UNROLL + 32 * u + lane; rn[u] = i < n ? rw[i] : H_READ_PAD; }
         for (int b = b_lo; b < b_hi; ++b) {
             const int base = b * 32 * K2J_UNROLL + lane;
-            uint32_t r[K2J_UNROLL];
             #pragma unroll
-            for (int u = 0; u < K2J_UNROLL; ++u) r[u] = (base + 32 * u < pl.n) ? rw[base + 32 * u] : H_READ_PAD;
+            for (int u = 0; u < K2J_UNROLL; ++u) r[u] = rn[u];
+            if (b + 1 < b_hi) {
+                #pragma unroll
+                for (int u = 0; u < K2J_UNROLL; ++u) { const int i = base + 32 * K2J_UNROLL + 32 * u; rn[u] = i < n ? rw[i] : H_READ_PAD; }
+            }
             if (!waited) { mbar_wait(&s_bar, 0); waited = true; }
+            // step 1: membership test, survivors compacted into the list
             #pragma unroll
             for (int u = 0; u < K2J_UNROLL; ++u) {
                 const uint32_t word = r[u];
@@ -257,11 +232,56 @@ k2_join_match(const K2JParams p)
                 const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass);
                 if (pass) list[ln + __popc(pm & lt)] = make_uint2(word, (uint32_t)(base + 32 * u));
                 ln += __popc(pm);
-                if (u & 1) { while (ln >= 32) round(32); }
+            }
+            // step 2: full rounds of 32 survivors (the plot's last block also takes the remainder)
+            const bool last = b + 1 == b_hi;
+            while (ln >= 32 || (last && ln > 0)) {
+                const int n_act = min(ln, 32);
+                __syncwarp();
+                const bool have = lane < n_act;
+                ln -= n_act;
+                const uint2 e = have ? list[ln + lane] : make_uint2(H_READ_PAD, 0u);
+                __syncwarp();                            // everybody holds its survivor before the list is written again
+                const uint32_t word = e.x;
+                uint32_t idx = 0, end = 0;
+                if (have) {
+                    const uint32_t ka = a_off + 2u * ((word & 0x3FFFFFFFu) >> shift);
+                    idx = k2j_lds16(ka); end = k2j_lds16(ka + 2u);
+                }
+                evaluated += end - idx;
+                int m0 = -1, m1 = -1, m2 = -1;           // first two equal entries; m2: where a third one sits (repeats)
+                for (; idx < end; ++idx) {
+                    if (k2j_lds32(a_tw + 4u * idx) == word) {
+                        if (m0 < 0) m0 = (int)idx; else if (m1 < 0) m1 = (int)idx; else { m2 = (int)idx; break; }
+                    }
+                }
+                int x0 = -1, x1 = -1;
+                if (m0 >= 0) x0 = xoff + (int)k2j_lds16(a_tp + 2u * (uint32_t)m0);      // negative: before the cut, not a cell of the plot
+                if (m1 >= 0) x1 = xoff + (int)k2j_lds16(a_tp + 2u * (uint32_t)m1);
+                const unsigned b0 = __ballot_sync(0xFFFFFFFFu, x0 >= 0), b1 = __ballot_sync(0xFFFFFFFFu, x1 >= 0);
+                if (x0 >= 0) queue[qn + __popc(b0 & lt)] = make_uint2((uint32_t)x0 | (word & 0xC0000000u), e.y);
+                qn += __popc(b0);
+                if (x1 >= 0) queue[qn + __popc(b1 & lt)] = make_uint2((uint32_t)x1 | (word & 0xC0000000u), e.y);
+                qn += __popc(b1);
+                if (__any_sync(0xFFFFFFFFu, m2 >= 0)) {  // rare: a word that sits three or more times in its bucket
+                    uint32_t i2 = m2 >= 0 ? (uint32_t)m2 : end;
+                    while (true) {
+                        int x = -1;
+                        while (i2 < end && x < 0) {
+                            const uint32_t ii = i2++;
+                            if (k2j_lds32(a_tw + 4u * ii) == word) x = xoff + (int)k2j_lds16(a_tp + 2u * ii);
+                        }
+                        const unsigned bb = __ballot_sync(0xFFFFFFFFu, x >= 0);
+                        if (bb == 0u) break;
+                        if (qn + 32 > K2J_QCAP) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
+                        if (x >= 0) queue[qn + __popc(bb & lt)] = make_uint2((uint32_t)x | (word & 0xC0000000u), e.y);
+                        qn += __popc(bb);
+                    }
+                }
+                if (qn > K2J_QCAP - 64 || (last && ln == 0 && qn > 0)) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }
             }
         }
-        if (ln > 0) round(ln);                           // the plot's last survivors (fewer than 32)
-        if (qn > 0) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; }
+        if (qn > 0) { __syncwarp(); k2_flush(st, queue, qn, lane); qn = 0; __syncwarp(); }   // (a last block without survivors)
     }
     if (!waited) mbar_wait(&s_bar, 0);                   // nobody leaves while the bulk copy may still be landing
     unsigned long long ev = evaluated;
