@@ -357,6 +357,12 @@ def run_gpu_arm(args):
     def sum_over_ranks(x):
         return reduce(x, dist.ReduceOp.SUM) if dist is not None else x
 
+    numa_node = None
+    if world > 1 and not args.no_numa_bind:
+        # one process per GPU: pinned buffers and planning threads on the NUMA node the GPU hangs off (no-op when the host
+        # shows no topology); the CPU baseline runs only at N = 1 and is never restricted
+        from vapor_b200.engine import bind_to_gpu_numa
+        numa_node = bind_to_gpu_numa(local_rank)
     eng = Engine(local_rank)
     opts = {}
     if args.tile_variant >= 0:
@@ -576,7 +582,7 @@ def run_gpu_arm(args):
             "phase_ms_per_step": {"pack": acc["pack_ms"] / K, "table": acc["table_ms"] / K, "tile": acc["tile_ms"] / K,
                                   "score": acc["score_ms"] / K, "genotype": acc["genotype_ms"] / K},
             "wall_ms_per_step_resident": 1e3 * wall_resident / args.steps,
-            "hits_per_step_rank0": int(tm_last["hits"]), "workload_gen_s": t_gen,
+            "hits_per_step_rank0": int(tm_last["hits"]), "workload_gen_s": t_gen, "numa_node_rank0": numa_node,
             "k2_mode": mode, "n_waves_rank0": n_waves, "overflow_plots_rank0": int(tm_last["n_overflow_plots"]),
             "sv_called": {"gt_0/0": int((gathered.sv_gt == 0).sum()), "gt_0/1": int((gathered.sv_gt == 1).sum()),
                           "gt_1/1": int((gathered.sv_gt == 2).sum()), "NA": int((gathered.sv_gt == 255).sum())},
@@ -620,6 +626,7 @@ def main():
     ap.add_argument("--tile-variant", type=int, default=-1, help="tile-kernel inner loop (-1 = library default)")
     ap.add_argument("--k2-mode", type=int, default=-1, help="kernel 2: 1 = join (library default), 0 = all-pairs tile kernel")
     ap.add_argument("--k3-mode", type=int, default=-1, help="kernel 3: 1 = warp per task (library default), 0 = CTA per task everywhere")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind each rank to its GPU's NUMA node")
     ap.add_argument("--opt", action="append", default=[], help="library tunable name=value (vapor_gpu_set_option), repeatable")
     ap.add_argument("--hit-budget-gb", type=float, default=0, help="device memory for the hit slab of one wave (0 = library default)")
     ap.add_argument("--k2-ctas-per-sm", type=int, default=0, help="persistent-grid size of the tile kernel (0 = occupancy)")

@@ -197,6 +197,9 @@ uint64_t vapor_hit_mix(uint32_t x, uint32_t y);
 
 int vapor_b200_abi_version(void);
 int vapor_gpu_device_count(void);     /* CUDA devices visible to this process (0 without a driver) */
+/* PCI bus id of a device ("0000:1b:00.0", NUL-terminated) into buf[len]: lets a one-process-per-GPU launcher bind each
+ * process to the NUMA node its GPU hangs off before it allocates pinned buffers (vapor_b200.engine.bind_to_gpu_numa). */
+int vapor_gpu_pci_bus_id(int device, char* buf, int len);
 
 #ifdef __cplusplus
 }

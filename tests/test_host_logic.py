@@ -246,3 +246,37 @@ def test_host_plan_independent_of_thread_count():
                 assert got["digest"] == base["digest"] and got["waves"] == base["waves"], (mode, budget, th)
     cx = synth.make_workload(28, seed=5, recipe="complex", size_range=(200, 900), reads_per_sv=3)
     assert host_plan(cx.batch, 1, 1)["digest"] == host_plan(cx.batch, 1, 4)["digest"]
+
+
+def test_bind_to_gpu_numa_reads_sysfs_and_is_a_noop_without_topology(tmp_path, monkeypatch):
+    """engine.bind_to_gpu_numa: the CPU list of the GPU's NUMA node from a (fake) sysfs tree; None, and no affinity
+    change, when the bus id or the node is not visible."""
+    import os
+    from vapor_b200 import engine
+
+    class FakeLib:
+        def __init__(self, bus, rc=0): self.bus, self.rc = bus, rc
+        def vapor_gpu_pci_bus_id(self, dev, buf, n):
+            buf.value = self.bus.encode()
+            return self.rc
+    orig = os.sched_getaffinity(0)
+    cpu = sorted(orig)[0]
+    (tmp_path / "bus/pci/devices/0000:1b:00.0").mkdir(parents=True)
+    (tmp_path / "bus/pci/devices/0000:1b:00.0/numa_node").write_text("1\n")
+    (tmp_path / "devices/system/node/node1").mkdir(parents=True)
+    (tmp_path / "devices/system/node/node1/cpulist").write_text(f"{cpu}-{cpu},9999\n")
+    assert engine._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    try:
+        monkeypatch.setattr(engine.N, "load", lambda: FakeLib("0000:1B:00.0"))
+        assert engine.bind_to_gpu_numa(0, sysfs=str(tmp_path)) == 1
+        assert os.sched_getaffinity(0) == {cpu}
+        os.sched_setaffinity(0, orig)
+        (tmp_path / "bus/pci/devices/0000:1b:00.0/numa_node").write_text("-1\n")
+        assert engine.bind_to_gpu_numa(0, sysfs=str(tmp_path)) is None
+        monkeypatch.setattr(engine.N, "load", lambda: FakeLib("0000:ff:00.0"))
+        assert engine.bind_to_gpu_numa(0, sysfs=str(tmp_path)) is None
+        monkeypatch.setattr(engine.N, "load", lambda: FakeLib("", rc=-1))
+        assert engine.bind_to_gpu_numa(0, sysfs=str(tmp_path)) is None
+        assert os.sched_getaffinity(0) == orig
+    finally:
+        os.sched_setaffinity(0, orig)

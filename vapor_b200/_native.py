@@ -23,6 +23,7 @@ EXPORTS = [
     "vapor_gpu_score", "vapor_gpu_upload", "vapor_gpu_run", "vapor_gpu_fetch",
     "vapor_gpu_last_timings", "vapor_gpu_dotdata", "vapor_gpu_selfplot_qc", "vapor_gpu_summarize", "vapor_gpu_host_alloc", "vapor_gpu_host_free",
     "vapor_gpu_int_peak", "vapor_host_plan", "vapor_hit_mix", "vapor_b200_abi_version", "vapor_gpu_device_count",
+    "vapor_gpu_pci_bus_id",
 ]
 
 
@@ -105,5 +106,7 @@ def load() -> C.CDLL:
     lib.vapor_hit_mix.restype = C.c_uint64
     lib.vapor_b200_abi_version.argtypes = []
     lib.vapor_gpu_device_count.argtypes = []
+    lib.vapor_gpu_pci_bus_id.argtypes = [C.c_int, C.c_char_p, C.c_int]
+    lib.vapor_gpu_pci_bus_id.restype = C.c_int
     _lib = lib
     return lib

@@ -203,7 +203,10 @@ def _shard_worker(job):
     """Worker process of the multi-GPU command line: one process per GPU, its own Session, its share of the events."""
     device, specs = job
     from ._native import load
-    sess = SF.Session(device % max(1, load().vapor_gpu_device_count()))      # more workers than GPUs: share them
+    from .engine import bind_to_gpu_numa
+    dev = device % max(1, load().vapor_gpu_device_count())                    # more workers than GPUs: share them
+    bind_to_gpu_numa(dev)                                                     # pinned buffers on the GPU's NUMA node
+    sess = SF.Session(dev)
     SF.set_session(sess)
     try:
         return _run_chunked(sess, specs), dict(sess.stats)

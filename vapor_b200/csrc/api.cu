@@ -1317,6 +1317,11 @@ int vapor_gpu_device_count(void) {
 
 uint64_t vapor_hit_mix(uint32_t x, uint32_t y) { return hit_mix(x, y); }
 
+int vapor_gpu_pci_bus_id(int device, char* buf, int len) {
+    if (!buf || len < 13) return VAPOR_E_ARG;
+    return cudaDeviceGetPCIBusId(buf, len, device) == cudaSuccess ? VAPOR_OK : VAPOR_E_CUDA;
+}
+
 const char* vapor_gpu_last_error(void* handle) {
     if (!handle) return g_open_error.c_str();
     return static_cast<Handle*>(handle)->err.c_str();

@@ -68,10 +68,13 @@ struct Task {              // one read of one SV/allele
 // shared-memory load.
 // One blob per chunk, staged into shared memory by one TMA bulk copy:
 //   uint32 word[Lp] | uint16 pos[Lp] | uint16 off[2^bits + 8] | uint32 filter[2^fbits / 32]      Lp = len rounded up to 8
-constexpr int K2J_CH       = 8192;             // positions per table chunk (pos fits 16 bits; blob <= 66 KB)
+#ifndef K2J_CH_N
+#define K2J_CH_N 8192
+#endif
+constexpr int K2J_CH       = K2J_CH_N;         // positions per table chunk (pos fits 16 bits; blob <= 66 KB)
 constexpr int K2J_MIN_BITS = 8;
 #ifndef K2J_MAX_BITS_N
-#define K2J_MAX_BITS_N 12
+#define K2J_MAX_BITS_N 13
 #endif
 constexpr int K2J_MAX_BITS = K2J_MAX_BITS_N;
 

@@ -357,8 +357,10 @@ __device__ void k3_clean_w10(const PlotView& v, K3Scratch& s, K3Shared& sh, Plot
         if (keep) {
             ++lcnt;
             const int x = (int)h.x;
-            // abs(float(x-y)/float(x)) < 0.16 for x > 0  (Simple_function.pyx:732-733)
-            if (x > 0 && fabs((double)(x - (int)y) / (double)x) < 0.16) ++l10;
+            // abs(float(x-y)/float(x)) < 0.16 for x > 0  (Simple_function.pyx:732-733) as the exact integer test
+            // 25 |x-y| < 4 x: a quotient of two integers below 2^28 that is not 4/25 differs from it by far more than an
+            // ulp, and an exact 4/25 rounds to the literal 0.16 itself (not below it)
+            if (x > 0 && 25ll * (long long)abs(x - (int)y) < 4ll * (long long)x) ++l10;
         }
     }
     #pragma unroll
@@ -378,8 +380,16 @@ __device__ void k3_clean_w10(const PlotView& v, K3Scratch& s, K3Shared& sh, Plot
 // and everything lands in the last bin when range == 0.
 __device__ __forceinline__ int k3_bin11(int d, int mn, int range) {
     if (range <= 0) return 10;
-    // d - mn <= range < 2^28 (sequence lengths are below 2^27), so 10 (d - mn) fits 32 unsigned bits: one 32-bit division
-    return (int)((10u * (uint32_t)(d - mn)) / (uint32_t)range);
+    // d - mn <= range < 2^28 (sequence lengths are below 2^27), so 10 (d - mn) fits 32 unsigned bits.  The quotient is at
+    // most 10: a single-precision estimate is off by less than one, two integer multiplies put it right (a 32-bit
+    // division is ~20 instructions and this runs six times per dot of a REDEF task).
+    const uint32_t num = 10u * (uint32_t)(d - mn), den = (uint32_t)range;
+    if (num > 10u * den) return 11;                             // only for a d outside [mn, mn + range]: no bin
+    int q = (int)((float)num * __frcp_rn((float)den));
+    q = min(max(q, 0), 10);
+    if ((uint32_t)q * den > num) --q;
+    else if ((uint32_t)(q + 1) * den <= num) ++q;
+    return q;
 }
 
 // dis_to_diagnal_most_abundant_defined + eu_dis_dir_calcu on the clean dots (Simple_function.pyx:582-591,
@@ -495,10 +505,11 @@ __device__ void k3_redef_stat(const PlotView& v, K3Scratch& s, K3Shared& sh, Plo
             const long long y = (long long)(h.y & HIT_Y_MASK);
             const long long B = 2ll * (long long)h.x + icpt2;
             const long long A = B - 2ll * y;
-            double ratio;
-            if (B == 0) ratio = fabs(((double)A * 0.5) / 1.0);       // x' == 0: divide by x'+1
-            else        ratio = fabs((double)A / (double)B);          // == (A/2)/(B/2) exactly
-            if (ratio > 0.1) { lsum += A; ++lcnt; }
+            // |(A/2) / (B/2)| > 0.1 (x' == 0: |A/2| / 1 > 0.1, i.e. A != 0) as the exact integer test 10 |A| > |B|: the
+            // quotient of two integers below 2^30 that is not 1/10 differs from it by far more than an ulp, and an exact
+            // 1/10 rounds to the literal 0.1 itself (not above it)
+            const bool far = (B == 0) ? (A != 0) : (10ll * llabs(A) > llabs(B));
+            if (far) { lsum += A; ++lcnt; }
         }
     }
     #pragma unroll

@@ -415,6 +415,41 @@ class Pipeline:
         return out
 
 
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device: int, sysfs: str = "/sys") -> Optional[int]:
+    """Restrict this process to the CPUs of the NUMA node GPU ``device`` hangs off, so that the pinned buffers it
+    allocates afterwards are first-touched on that node and its H2D copies do not cross the socket interconnect (with one
+    process per GPU, eight ranks otherwise pull their inputs through whichever node they happened to start on).
+    Returns the node, or None when the topology is not visible (single node, container without sysfs, no GPU): a no-op
+    then.  Reads ``<sysfs>/bus/pci/devices/<bus id>/numa_node`` and ``<sysfs>/devices/system/node/node<N>/cpulist``."""
+    import os
+    try:
+        buf = C.create_string_buffer(32)
+        if N.load().vapor_gpu_pci_bus_id(int(device), buf, 32) != 0:
+            return None
+        bus = buf.value.decode().lower()
+        node = int(open(os.path.join(sysfs, "bus/pci/devices", bus, "numa_node")).read().strip())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open(os.path.join(sysfs, "devices/system/node", f"node{node}", "cpulist")).read())
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def host_plan(batch: PackedBatch, k2_mode: int = 1, threads: int = 0, wave_budget_bytes: int = 0) -> dict:
     """``vapor_host_plan``: plan a batch on the host only (no GPU needed): wall ms, plan digest, counts."""
     lib = N.load()
