@@ -495,8 +495,9 @@ def run_gpu_arm(args):
                                     "cells_nominal": int(tm_last["cells"]), "cells_evaluated": int(tm_last["evaluated_cells"]),
                                     "evaluated_cells_per_s": tm_last["evaluated_cells"] / tile_s,
                                     "read_words_probed_per_s": n_words / tile_s,
-                                    "note": "radix-partitioned join: a read k-mer is compared only with the table bucket it falls into; the kernel is "
-                                            "bound by instruction issue and shared-memory latency of the probe loop, not by HBM or the compare count"}
+                                    "note": "radix-partitioned join: a read k-mer first meets the table's membership bitmap; the survivors (one in three) "
+                                            "are compacted into full-warp rounds, each against the bucket it falls into; bound by global-load latency and "
+                                            "instruction issue (ncu: issue slots 51-54 % busy), not by HBM or the compare count"}
         table_s = tm_last["table_ms"] * 1e-3
         if table_s > 0:
             alg1b = table_bytes * 10.0 / 6.0            # 4 B/word read + 6 B/word (+ offsets) written
@@ -508,7 +509,9 @@ def run_gpu_arm(args):
         alg3 = 8.0 * tm_last["hits"] + 77.0 * batch.n_task
         kernels["k3_score_reads"] = {"bound": "hbm", "ms": 1e3 * score_s, "algorithmic_bytes": alg3, "achieved": alg3 / score_s / 1e9, "peak": hbm_peak,
                                      "unit": "GB/s", "frac": alg3 / score_s / 1e9 / hbm_peak,
-                                     "note": "reads every hit once (8 B) and writes 77 B per read; latency-bound on short phases per read"}
+                                     "launches": "k3w_score_reads (one warp per task, value ranges <= 8192 bins) + k3_score_reads (one CTA per task, larger ranges)",
+                                     "note": "must read every hit once (8 B) and write 77 B per read; really 4-10 passes over a plot's hits (L2-resident) with short "
+                                             "dependent phases: bound by latency and instruction issue"}
     dom = max(kernels, key=lambda n: kernels[n]["ms"])
     step_ms = acc["total_ms"] / K
     roofline = dict(kernels[dom])

@@ -336,3 +336,32 @@ def test_pipeline_double_buffered(engine):
     for g, e in zip(got, exp):
         for f in e.__dataclass_fields__:
             np.testing.assert_array_equal(getattr(g, f), getattr(e, f), err_msg=f)
+
+
+def test_kernel3_variants_and_overlap_agree(engine):
+    """Kernel 3 has two implementations (one warp per task, k3_warp.cuh; one CTA per task, k3_score.cuh) and the run can
+    put kernel 3 of a wave on a second stream under kernels 1-2 of the next wave: every combination gives byte-identical
+    results on a workload of every simple SV type, mode and k, lower case and miss_bp > 0 included -- with all five
+    scratch classes on the warp kernel, with none, and with the default split -- and a sample agrees with the oracle."""
+    from vapor_b200.engine import Engine
+    w = synth.make_workload(160, seed=4711, size_range=(50, 5000), reads_per_sv=12, max_miss=4, lowercase_every=7,
+                            k_choices=(10, 10, 20, 10, 30, 10, 40))
+    base = engine.score(w.batch)
+    other = Engine(0, hit_budget_bytes=48 << 20)            # several waves, so that the overlap has something to overlap
+    try:
+        other.set_option("k2_mode", 1 if engine.k2_mode_name == "join" else 0)
+        for opts in ({"k3_mode": 0}, {"k3_mode": 1, "k3_warp_classes": 5}, {"k3_mode": 1, "k3_warp_classes": 1},
+                     {"k3_mode": 1, "k3_warp_classes": 3, "overlap": 1}, {"k3_mode": 0, "overlap": 1}):
+            for k_, v_ in opts.items():
+                other.set_option(k_, v_)
+            got = other.score(w.batch)
+            assert other.timings()["n_waves"] > 1
+            for f in base.__dataclass_fields__:
+                np.testing.assert_array_equal(getattr(got, f), getattr(base, f), err_msg=f"{opts} {f}")
+            again = other.score(w.batch)                     # the same handle, the same resident buffers, a second time
+            for f in base.__dataclass_fields__:
+                np.testing.assert_array_equal(getattr(again, f), getattr(base, f), err_msg=f"{opts} second run {f}")
+    finally:
+        other.close()
+    sample = w.batch.shard([1, 2, 3, 4, 50, 99, 140])
+    _compare(engine.score(sample), BO.score_batch(sample))
