@@ -2,7 +2,7 @@
 """SASS evidence for profiles/: the TMA prologue and hot loops of the kernel-2 variants, cut out of
 `cuobjdump -sass vapor_b200/csrc/libvapor_b200.so` (no GPU needed).
 
-    python tools/sass_extract.py            -> profiles/r02_k2_tile_hot_loop.sass, profiles/r02_k2_join_probe_loop.sass"""
+    python tools/sass_extract.py            -> profiles/r02_k2_tile_hot_loop.sass, profiles/r02g_k2_join_probe_loop.sass"""
 import os
 import re
 import subprocess
@@ -48,7 +48,7 @@ def write(path, header, blocks):
 def main():
     fns = functions()
     tile = next(v for k, v in fns.items() if "k2_tile_matchILi13ELi2E" in k)
-    join = next(v for k, v in fns.items() if "k2_join_match" in k)
+    join = next(v for k, v in fns.items() if "k2_join_matchILi8E" in k)
     # tile kernel: TMA issue (UBLKCP) + mbarrier wait (SYNCS), then the first vote block of the hot loop = from the first
     # LDS.128 after the wait to the first VOTE
     i_tma = next(i for i, (_, t) in enumerate(tile) if "UBLKCP" in t)
@@ -65,20 +65,27 @@ def main():
     write(os.path.join(ROOT, "profiles", "r02_k2_tile_hot_loop.sass"), hdr,
           [("TMA staging of the streamed chunk", tile[max(0, i_tma - 6):i_tma + 2]), ("mbarrier wait", tile[i_wait - 1:i_wait + 3]),
            ("one vote block of the hot loop (LDS.128 ... VOTE)", loop)])
-    # join kernel: UBLKCP + wait, then the probe: bucket offsets (two LDS.U16), entry compare loop, queue slot (ATOMS)
+    # join kernel: UBLKCP + wait, then step 1 (membership test of one word: LDS of the bitmap word ... VOTE + STS of the survivor)
+    # and step 2 (one round: two LDS.U16 bucket offsets, the entry scan, the two VOTEs that park the matched cells)
     j_tma = next(i for i, (_, t) in enumerate(join) if "UBLKCP" in t)
     j_wait = next(i for i, (_, t) in enumerate(join) if i > j_tma and "SYNCS" in t and "TRYWAIT" in t)
-    j_u16 = next(i for i, (_, t) in enumerate(join) if i > j_wait and "LDS.U16" in t)
-    j_atom = next(i for i, (_, t) in enumerate(join) if i > j_u16 and t.split()[-1] != "" and ("ATOMS" in t))
-    j_end = next(i for i, (_, t) in enumerate(join) if i > j_atom and "VOTE" in t)
-    probe = join[j_u16 - 4:j_end + 1]
-    hdr = ("// k2_join_match (radix-partitioned join, k2_mode 1, the default), sm_100a, from cuobjdump -sass of the in-tree library.\n"
-           f"// kernel: {len(join)} instructions.  One probe of one read k-mer word per lane: {mnemonic_counts(probe)}\n"
-           "// UBLKCP = the single TMA bulk copy that stages the table blob of the CTA; LDS.U16 x2 = bucket offsets;\n"
-           "// LDS + ISETP = entry compare; ATOMS = queue slot for a matched cell.\n")
-    write(os.path.join(ROOT, "profiles", "r02_k2_join_probe_loop.sass"), hdr,
+    j_f = next(i for i, (_, t) in enumerate(join) if i > j_wait and re.match(r"(@!?U?P\d+ )?LDS ", t))
+    j_fv = next(i for i, (_, t) in enumerate(join) if i > j_f and "VOTE" in t)
+    j_fs = next(i for i, (_, t) in enumerate(join) if i > j_fv and "STS" in t)
+    filt = join[j_f - 4:j_fs + 1]
+    j_u16 = next(i for i, (_, t) in enumerate(join) if i > j_fs and "LDS.U16" in t)
+    votes = [i for i, (_, t) in enumerate(join) if i > j_u16 and "VOTE" in t]
+    rnd = join[j_u16 - 4:votes[1] + 6]
+    hdr = ("// k2_join_match<8> (radix-partitioned join with membership pre-filter, k2_mode 1, the default), sm_100a, from cuobjdump -sass of\n"
+           f"// the in-tree library.  kernel: {len(join)} instructions.\n"
+           f"// step 1, one read k-mer word per lane against the membership bitmap: {mnemonic_counts(filt)}\n"
+           f"// step 2, one round of 32 survivors against their buckets: {mnemonic_counts(rnd)}\n"
+           "// UBLKCP = the single TMA bulk copy that stages the table blob of the CTA; LDS = bitmap word; VOTE + POPC + STS.64 = survivor\n"
+           "// compaction; LDS.U16 x2 = bucket offsets; LDS + ISETP = entry compare; VOTE x2 = queue slots of the matched cells (no atomics).\n")
+    write(os.path.join(ROOT, "profiles", "r02g_k2_join_probe_loop.sass"), hdr,
           [("TMA staging of the table blob", join[max(0, j_tma - 6):j_tma + 2]), ("mbarrier wait", join[j_wait - 1:j_wait + 3]),
-           ("probe of the first of four words per lane (bucket lookup ... end-of-round vote)", probe)])
+           ("step 1: membership test of the first of four words per lane, survivors compacted into the list", filt),
+           ("step 2: one round (bucket lookup, entry scan, matched cells parked by ballot)", rnd)])
 
 
 if __name__ == "__main__":

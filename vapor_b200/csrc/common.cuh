@@ -74,7 +74,7 @@ struct Task {              // one read of one SV/allele
 constexpr int K2J_CH       = K2J_CH_N;         // positions per table chunk (pos fits 16 bits; blob <= 66 KB)
 constexpr int K2J_MIN_BITS = 8;
 #ifndef K2J_MAX_BITS_N
-#define K2J_MAX_BITS_N 13
+#define K2J_MAX_BITS_N 12
 #endif
 constexpr int K2J_MAX_BITS = K2J_MAX_BITS_N;
 
