@@ -446,6 +446,7 @@ def run_gpu_arm(args):
     pipe.map([batch] * args.steps, [res2[i % 2] for i in range(args.steps)], after=gather)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - te0)
+    stage_ms = {k_: round(1e3 * v_ / args.steps, 3) for k_, v_ in pipe.stage_s.items()}      # rank 0's, per step
     pipe.close()
     e2e_value = total_reads * args.steps / e2e_s
     launches_total = sum_over_ranks(float(acc["launches"]))
@@ -573,7 +574,7 @@ def run_gpu_arm(args):
                     "api": "vapor_b200.engine.Pipeline(depth=2).map: two handles, each step = vapor_gpu_upload + vapor_gpu_run + vapor_gpu_fetch on "
                            "pinned host buffers (host planning + H2D + kernels + D2H every step, the steps of the two handles interleaved), "
                            "then multi.scatter_part into the shared input-order result arrays (N > 1)",
-                    "bytes_are": "per rank (rank 0)",
+                    "bytes_are": "per rank (rank 0)", "pipeline_stage_ms_rank0": stage_ms,
                     "single_blocking_call": {"value": total_reads * args.steps / e2e_single_s, "ms_per_step": 1e3 * e2e_single_s / args.steps,
                                              "host_prep_ms": tm_e2e["host_prep_ms"], "h2d_ms": tm_e2e["h2d_ms"], "d2h_ms": tm_e2e["d2h_ms"]}},
             "gpu_launches": int(launches_total),

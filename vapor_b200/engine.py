@@ -377,8 +377,10 @@ class Pipeline:
         ``after(results_i)`` (optional) runs in the worker thread right after batch i was scored -- e.g. the scatter
         of a shard's results into shared input-order arrays -- while the other handle keeps the GPU busy."""
         import threading
+        import time
         batches = list(batches)
         n = len(batches)
+        self.stage_s = {}
         out: List[Optional[Results]] = [None] * n
         errs: List[BaseException] = []
         nxt = [0]
@@ -394,14 +396,26 @@ class Pipeline:
                     return
                 try:
                     into = results[i] if results is not None and results[i] is not None else _alloc_results(batches[i].n_task, batches[i].n_sv)
+                    t0 = time.perf_counter()
                     with copy_in:
+                        t1 = time.perf_counter()
                         eng.upload(batches[i])
+                        t2 = time.perf_counter()
                     with kernels:
+                        t3 = time.perf_counter()
                         eng.run()
+                        t4 = time.perf_counter()
                     with copy_out:
+                        t5 = time.perf_counter()
                         out[i] = eng.fetch(into)
+                        t6 = time.perf_counter()
                     if after is not None:
                         after(out[i])
+                    t7 = time.perf_counter()
+                    with lock:                           # wall seconds per stage, summed over the batches (self.stage_s)
+                        for k_, v_ in (("wait_upload", t1 - t0), ("upload", t2 - t1), ("wait_run", t3 - t2), ("run", t4 - t3),
+                                       ("wait_fetch", t5 - t4), ("fetch", t6 - t5), ("after", t7 - t6)):
+                            self.stage_s[k_] = self.stage_s.get(k_, 0.0) + v_
                 except BaseException as e:          # noqa: BLE001
                     errs.append(e)
                     return
