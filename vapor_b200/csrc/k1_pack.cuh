@@ -24,8 +24,11 @@
 
 namespace vb {
 
-constexpr int K1_THREADS = 256;
-constexpr int K1_CHUNK   = 2048;          // positions per CTA
+#ifndef K1_THREADS_N
+#define K1_THREADS_N 256
+#endif
+constexpr int K1_THREADS = K1_THREADS_N;
+constexpr int K1_CHUNK   = 8 * K1_THREADS; // positions per CTA (8 per thread)
 constexpr int K1_MAXK    = 40;
 
 __constant__ uint8_t c_code_lut[256];
@@ -276,7 +279,7 @@ k1_pack_kmers(const uint8_t* __restrict__ seq, const Operand* __restrict__ ops,
     __shared__ __align__(4) uint16_t s_p2[K1_PACK_GROUPS + 2];   // 2-bit codes, 8 bases per entry (k <= 15)
     __shared__ __align__(4) uint8_t s_np[K1_PACK_GROUPS + 8];    // "not plain ACGT" bits, 8 bases per entry
     __shared__ __align__(4) uint8_t s_inv[K1_PACK_GROUPS + 8];   // "invalid character" bits
-    s_lut[threadIdx.x] = c_code_lut[threadIdx.x];
+    for (int i = threadIdx.x; i < 256; i += K1_THREADS) s_lut[i] = c_code_lut[i];
     const int bid = blockIdx.x;
     const int lo = cta_op[bid];
     const Operand op = ops[lo];
