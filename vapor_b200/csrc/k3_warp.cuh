@@ -2,12 +2,14 @@
 //
 // Same reference functions as k3_score.cuh (vapor_vali/Simple_function.pyx:182-203, 241-257, 277-294, 404-448,
 // 551-591, 705-733, 788-792, 1104-1118, 1718-1726, 1913-1915) and the same bitmap chain-grouping, re-cut for tasks
-// whose value range fits 26 624 bins (every simple SV up to 5 kb; larger windows stay on the CTA-per-task kernel):
+// with small value ranges.  It can take ranges up to 26 624 bins; by default it gets the classes up to 8 192 bins
+// (63 % of the tasks of a 50 bp - 5 kb SV list), where it needs 23 ns per task against 63 ns for the CTA kernel -- above
+// that its scratch leaves too few warps per SM and the CTA-per-task kernel wins (api.cu, k3w_nclass):
 //
 //   * a task is a few hundred to a few thousand dots.  With 256 threads on it, two thirds of the instructions of the
 //     CTA kernel were fixed cost per phase (about 70 phases per task: barriers, block reductions through shared
 //     atomics, scans of short arrays) and every phase exposed one global-memory latency.  A warp pays a shuffle
-//     reduction per phase, keeps four 256-byte loads in flight per pass, and 16-32 tasks are resident per SM
+//     reduction per phase, keeps four 256-byte loads in flight per pass, and 32 tasks are resident per SM
 //     instead of 6;
 //   * scratch per task is 0.78 bytes per bin instead of 1.95: the group-start bitmap overwrites the occupancy
 //     bitmap in place (the neighbour word travels by shuffle), word prefixes and group sizes are 16-bit (a plot of
@@ -19,6 +21,9 @@
 //     (|x-y|/x < 0.16  <=>  25|x-y| < 4x;  |A/B| > 0.1  <=>  10|A| > |B|: the quotient of two integers below 2^20
 //     that differs from 4/25 or 1/10 differs by far more than an ulp, and an exact 4/25 or 1/10 rounds to the
 //     literal itself), the 11-edge binning by a float estimate corrected with two integer multiplies;
+//   * every pass body exists once (the four dots in flight rotate through one register pair) and the three stages
+//     have one call site each: with the bodies unrolled four times the kernel was 180 KB of code and instruction
+//     fetch was its first stall reason;
 //   * tasks are pulled from a per-launch queue (one atomic per task), so warps never wait for the slowest
 //     task of a CTA.
 // Results are bit-identical to the CTA kernel's (all GPU tests and the soak run both through the oracle).
