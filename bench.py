@@ -516,16 +516,35 @@ def run_gpu_arm(args):
     dom = max(kernels, key=lambda n: kernels[n]["ms"])
     step_ms = acc["total_ms"] / K
     roofline = dict(kernels[dom])
-    # DRAM traffic of the dominant kernel: measured by ncu (dram__bytes_read + dram__bytes_write, summed over the kernel's launches
-    # of one run) on 2 000 SVs of config 2 -- quoted as `traffic` only when this run is that very workload, never scaled
+    # DRAM traffic of the dominant kernel, measured by ncu --set full (dram__bytes_read + dram__bytes_write), per launch like
+    # `achieved`.  Two captures exist: one WAVE of the default workload (a wave of the 100k-SV list = 6 250 SVs; the wave's
+    # launches of the kernel averaged) -- quoted as `traffic` when this run consists of such waves -- and a whole run of 2 000 SVs
+    # of config 2, quoted only for that very workload.  Nothing is scaled.
     traffic, traffic_profile = None, None
-    try:
-        tp = json.load(open(os.path.join(ROOT, "profiles", "r02g_traffic.json")))
+    n_launch_dom = {"k1_pack_kmers": 1, "k1b_build_tables": 1, "k2_join_match": 3, "k2_tile_match": 1, "k3_score_reads": 5}.get(dom, 1) * n_waves
+    roofline["launches_per_step"] = n_launch_dom
+    roofline["algorithmic_bytes_per_launch"] = roofline.get("algorithmic_bytes", 0.0) / max(1, n_launch_dom) if "algorithmic_bytes" in roofline else None
+    roofline["ms_per_launch"] = roofline["ms"] / max(1, n_launch_dom)
+
+    def _kernel_traffic(tp):
         kt = tp["kernels"].get(dom)
         if kt and dom == "k3_score_reads" and "k3w_score_reads" in tp["kernels"]:      # the score phase is two kernels
             kw = tp["kernels"]["k3w_score_reads"]
             kt = {k_: kt[k_] + kw[k_] for k_ in ("launches", "dram_bytes_read", "dram_bytes_write", "ms")}
-        if kt:
+        return kt
+    try:
+        tw = json.load(open(os.path.join(ROOT, "profiles", "r02h_wave_traffic.json")))
+        kt = _kernel_traffic(tw)
+        if kt and args.config == tw["config"] and not args.weak and w.batch.n_sv >= tw["wave_svs"] and mode == 1:
+            traffic = (kt["dram_bytes_read"] + kt["dram_bytes_write"]) / max(1, kt["launches"])
+            traffic_profile = {"measured_on": tw["source"], "dram_bytes_per_wave": kt["dram_bytes_read"] + kt["dram_bytes_write"],
+                               "launches_per_wave": kt["launches"], "kernel_ms_under_ncu_per_wave": kt["ms"]}
+    except Exception:
+        pass
+    try:
+        tp = json.load(open(os.path.join(ROOT, "profiles", "r02g_traffic.json")))
+        kt = _kernel_traffic(tp)
+        if kt and traffic_profile is None:
             traffic_profile = {"measured_on": f"config {tp['config']}, {tp['n_sv']} SVs (ncu --set full)", "dram_bytes": kt["dram_bytes_read"] + kt["dram_bytes_write"],
                                "launches": kt["launches"], "kernel_ms_under_ncu": kt["ms"]}
             if args.config == tp["config"] and n_list == tp["n_sv"] and world == 1:

@@ -34,7 +34,10 @@ namespace vb {
 
 constexpr int K1B_THREADS = 256;
 constexpr int K2J_WARPS     = 8;                // warps per CTA (tables up to 44 KB: 4 CTAs per SM)
-constexpr int K2J_WARPS_BIG = 16;               // ... for the largest tables (2 CTAs per SM by shared memory: keep 32 warps per SM)
+#ifndef K2J_WARPS_BIG_N
+#define K2J_WARPS_BIG_N 12
+#endif
+constexpr int K2J_WARPS_BIG = K2J_WARPS_BIG_N;    // ... for the largest tables (2 CTAs per SM by shared memory): 12 warps at 85 registers beat 16 at 64 (measured, -2 %)
 constexpr int K2J_UNROLL  = 4;                  // read words per lane and step (loads in flight)
 #ifndef K2J_PLOTS_N
 #define K2J_PLOTS_N 24
