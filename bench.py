@@ -407,7 +407,7 @@ def run_gpu_arm(args):
     barrier()
     sampler = ClockSampler(local_rank)
     t0 = time.perf_counter()
-    acc = {"total_ms": 0.0, "tile_ms": 0.0, "pack_ms": 0.0, "table_ms": 0.0, "score_ms": 0.0, "genotype_ms": 0.0, "launches": 0}
+    acc = {"total_ms": 0.0, "tile_ms": 0.0, "pack_ms": 0.0, "table_ms": 0.0, "score_ms": 0.0, "score_warp_ms": 0.0, "genotype_ms": 0.0, "launches": 0}
     for _ in range(args.steps):
         eng.run()
         tm = eng.timings()
@@ -505,14 +505,35 @@ def run_gpu_arm(args):
             kernels["k1b_build_tables"] = {"bound": "hbm", "ms": 1e3 * table_s, "algorithmic_bytes": alg1b,
                                            "achieved": alg1b / table_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                            "frac": alg1b / table_s / 1e9 / hbm_peak}
+    # kernel 3 is two kernels: the warp-per-task one (value ranges up to 8 192 bins by default) and the CTA-per-task one; the library
+    # times them apart (score_warp_ms).  Which kernel a task goes to follows from its plots' value range n + m - 1 (api.cu,
+    # k3_class_of), so the hits each kernel must read are known exactly from the fetched per-task hit counts.
     score_s = acc["score_ms"] * 1e-3 / K
+    score_w_s = acc["score_warp_ms"] * 1e-3 / K
     if score_s > 0:
-        alg3 = 8.0 * tm_last["hits"] + 77.0 * batch.n_task
-        kernels["k3_score_reads"] = {"bound": "hbm", "ms": 1e3 * score_s, "algorithmic_bytes": alg3, "achieved": alg3 / score_s / 1e9, "peak": hbm_peak,
-                                     "unit": "GB/s", "frac": alg3 / score_s / 1e9 / hbm_peak,
-                                     "launches": "k3w_score_reads (one warp per task, value ranges <= 8192 bins) + k3_score_reads (one CTA per task, larger ranges)",
-                                     "note": "must read every hit once (8 B) and write 77 B per read; really 4-10 passes over a plot's hits (L2-resident) with short "
-                                             "dependent phases: bound by latency and instruction issue"}
+        seq_len = np.diff(batch.seq_off)
+        kk = batch.task_k.astype(np.int64)
+        n_read = np.maximum(0, seq_len[batch.task_read] - kk + 1)
+        miss = batch.task_miss.astype(np.int64)
+        nb_task = np.ones(batch.n_task, dtype=np.int64)
+        for which in (batch.task_ref, batch.task_alt):
+            ls = seq_len[which]
+            cut = np.where(miss >= 0, miss, np.maximum(0, ls + miss))
+            m_struct = np.maximum(0, ls - kk + 1 - cut)
+            nb_task = np.maximum(nb_task, n_read + m_struct - 1)
+        warp_cap = int(opts.get("k3_warp_classes", 3))
+        warp_cap = 0 if int(opts.get("k3_mode", 1)) == 0 or warp_cap == 0 else (2048, 4096, 8192, 16384, 26624)[warp_cap - 1]
+        on_warp = nb_task <= warp_cap
+        # every distinct plot's hits once: columns 2-3 repeat columns 0-1 when the W10 opinion looks at the same plots
+        hits_task = res.task_hits[:, :2].astype(np.int64).sum(axis=1)
+        note3 = ("must read every hit once (8 B) and write 77 B per read; really 4-10 passes over a plot's hits (L2-resident) with short "
+                 "dependent phases: bound by latency and instruction issue")
+        for name, sel, sec in (("k3w_score_reads", on_warp, score_w_s), ("k3_score_reads", ~on_warp, score_s - score_w_s)):
+            if sec <= 0 or not sel.any():
+                continue
+            algk = 8.0 * float(hits_task[sel].sum()) + 77.0 * float(sel.sum())
+            kernels[name] = {"bound": "hbm", "ms": 1e3 * sec, "algorithmic_bytes": algk, "achieved": algk / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": algk / sec / 1e9 / hbm_peak, "tasks": int(sel.sum()), "hits": int(hits_task[sel].sum()), "note": note3}
     dom = max(kernels, key=lambda n: kernels[n]["ms"])
     step_ms = acc["total_ms"] / K
     roofline = dict(kernels[dom])
@@ -521,17 +542,13 @@ def run_gpu_arm(args):
     # launches of the kernel averaged) -- quoted as `traffic` when this run consists of such waves -- and a whole run of 2 000 SVs
     # of config 2, quoted only for that very workload.  Nothing is scaled.
     traffic, traffic_profile = None, None
-    n_launch_dom = {"k1_pack_kmers": 1, "k1b_build_tables": 1, "k2_join_match": 3, "k2_tile_match": 1, "k3_score_reads": 5}.get(dom, 1) * n_waves
+    n_launch_dom = {"k1_pack_kmers": 1, "k1b_build_tables": 1, "k2_join_match": 3, "k2_tile_match": 1, "k3_score_reads": 2, "k3w_score_reads": 3}.get(dom, 1) * n_waves
     roofline["launches_per_step"] = n_launch_dom
     roofline["algorithmic_bytes_per_launch"] = roofline.get("algorithmic_bytes", 0.0) / max(1, n_launch_dom) if "algorithmic_bytes" in roofline else None
     roofline["ms_per_launch"] = roofline["ms"] / max(1, n_launch_dom)
 
     def _kernel_traffic(tp):
-        kt = tp["kernels"].get(dom)
-        if kt and dom == "k3_score_reads" and "k3w_score_reads" in tp["kernels"]:      # the score phase is two kernels
-            kw = tp["kernels"]["k3w_score_reads"]
-            kt = {k_: kt[k_] + kw[k_] for k_ in ("launches", "dram_bytes_read", "dram_bytes_write", "ms")}
-        return kt
+        return tp["kernels"].get(dom)
     try:
         tw = json.load(open(os.path.join(ROOT, "profiles", "r02h_wave_traffic.json")))
         kt = _kernel_traffic(tw)

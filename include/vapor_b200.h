@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VAPOR_B200_ABI_VERSION 2
+#define VAPOR_B200_ABI_VERSION 3
 
 /* error codes */
 #define VAPOR_OK            0
@@ -109,6 +109,8 @@ typedef struct vapor_timings {
     int32_t k2_mode;             /* kernel-2 variant the last plan was made for */
     int64_t table_bytes;         /* bytes of the sorted word tables kernel 1b writes and the join kernel stages (k2_mode 1) */
     int64_t probe_words;         /* read k-mer words the join kernel streams: sum of n over the non-empty plots */
+    float   score_warp_ms;       /* the part of score_ms spent in the warp-per-task kernel 3 (k3w_score_reads) */
+    int32_t pad_;
 } vapor_timings_t;
 
 /* Open one handle on CUDA device `device`.  One handle per device/thread; a handle is

@@ -23,7 +23,7 @@ def test_header_symbols_exported():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/vapor_b200.h but not exported"
     assert sorted(_native.EXPORTS) == declared
-    assert lib.vapor_b200_abi_version() == 2
+    assert lib.vapor_b200_abi_version() == 3
     # the native region extraction (include/vapor_hostio.h) lives in the same library
     from vapor_b200 import _hostio
     io_declared = _declared_functions("vapor_hostio.h")

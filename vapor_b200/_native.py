@@ -61,6 +61,7 @@ class vapor_timings_t(C.Structure):
         ("launches", C.c_int64), ("bases", C.c_int64), ("padded_cells", C.c_int64),
         ("evaluated_cells", C.c_int64), ("table_ms", C.c_float), ("k2_mode", C.c_int32),
         ("table_bytes", C.c_int64), ("probe_words", C.c_int64),
+        ("score_warp_ms", C.c_float), ("pad_", C.c_int32),
     ]
 
     def as_dict(self):

@@ -135,8 +135,8 @@ struct K2JParams {
 };
 
 #ifndef K2J_MINB
-#define K2J_MINB 4
-#endif
+#define K2J_MINB 3                               // 3 CTAs of 8 warps per SM at 85 registers: no spills in the probe loop; 4 at 64 registers
+#endif                                          // spilled the words in flight and was 3 % slower (measured)
 constexpr int K2J_QCAP = 96;                    // per-warp queue of matched cells awaiting emission
 constexpr int K2J_LCAP = 160;                   // per-warp list of read words that passed the filter (< 32 carried + 128 new)
 
