@@ -167,21 +167,44 @@ __device__ __forceinline__ uint32_t k3_groups_max(const K3Groups& s, int ng) {  
     return lmax;
 }
 
+// Pass 0 (span of x over all hits + checksum of the hit list) can ride on the first pass of a cleaning: the caller decides what
+// to clean from the hit counts alone and applies the span gates afterwards, so a plot's hits are read one time less.
+struct K3P0 { int minx, maxx; unsigned long long cs; };
+__device__ __forceinline__ void k3_p0_init(K3Shared& sh) { sh.imin = 0x7FFFFFFF; sh.imax = -1; sh.u64a = 0; }     // one thread, before a barrier
+__device__ __forceinline__ void k3_p0_reduce(K3Shared& sh, int lmin, int lmax, unsigned long long lsum) {          // every thread, before a barrier
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xFFFFFFFFu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xFFFFFFFFu, lmax, o));
+        lsum += __shfl_xor_sync(0xFFFFFFFFu, lsum, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&sh.imin, lmin); atomicMax(&sh.imax, lmax); atomicAdd(&sh.u64a, lsum); }
+}
+
 // Chain groups of the values binf(hit) in [0, nb) over the hits of a plot (binf < 0 = hit not taken): runs of
 // occupied values whose gaps are < 10, and their sizes.  On return k3_group_size(set, value) answers per value and
 // `gmax` (a field of sh) holds the largest group.  Every thread of the block must call it.
 template <typename BinF>
-__device__ void k3_build_groups(const uint2* hits, uint32_t H, K3Groups& s, int nb, K3Shared& sh, unsigned int K3Shared::*gmax, BinF binf) {
+__device__ void k3_build_groups(const uint2* hits, uint32_t H, K3Groups& s, int nb, K3Shared& sh, unsigned int K3Shared::*gmax, BinF binf,
+                                K3P0* p0 = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int W = (nb + 31) >> 5;
     k3_groups_clear(s, W);
-    if (tid == 0) sh.*gmax = 0;
+    if (tid == 0) { sh.*gmax = 0; if (p0) k3_p0_init(sh); }
     __syncthreads();
-    for (uint32_t i = tid; i < H; i += K3_THREADS) {
-        const int b = binf(hits[i]);
-        if (b >= 0) k3_groups_mark(s, b);
+    {
+        int lmin = 0x7FFFFFFF, lmax = -1;
+        unsigned long long lsum = 0;
+        for (uint32_t i = tid; i < H; i += K3_THREADS) {
+            const uint2 h = hits[i];
+            if (p0) { lmin = min(lmin, (int)h.x); lmax = max(lmax, (int)h.x); lsum += hit_mix(h.x, h.y & HIT_Y_MASK); }
+            const int b = binf(h);
+            if (b >= 0) k3_groups_mark(s, b);
+        }
+        if (p0) k3_p0_reduce(sh, lmin, lmax, lsum);
     }
     __syncthreads();
+    if (p0) { p0->minx = sh.imin; p0->maxx = sh.imax; p0->cs = sh.u64a; }
     k3_groups_starts(s, W);
     __syncthreads();
     k3_block_scan(s.wpref + 1, W, sh);
@@ -245,21 +268,28 @@ __device__ void k3_pass0(const PlotView& v, K3Shared& sh, int& minx, int& maxx, 
 
 // Chain groups of y-x into set D and of y+x into set A in one go: every hit is read twice instead of four times,
 // and both sets stay available, so no flag has to be written back between the two clusterings.
-__device__ void k3_build_groups_both(const PlotView& v, K3Scratch& s, K3Shared& sh) {
+__device__ void k3_build_groups_both(const PlotView& v, K3Scratch& s, K3Shared& sh, K3P0* p0) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int nb = v.n + v.m - 1, moff = v.m - 1;
     const int W = (nb + 31) >> 5;
     k3_groups_clear(s.D, W);
     k3_groups_clear(s.A, W);
-    if (tid == 0) { sh.gmaxD = 0; sh.gmaxA = 0; }
+    if (tid == 0) { sh.gmaxD = 0; sh.gmaxA = 0; if (p0) k3_p0_init(sh); }
     __syncthreads();
-    for (uint32_t i = tid; i < v.H; i += K3_THREADS) {
-        const uint2 h = v.hits[i];
-        const int x = (int)h.x, y = (int)(h.y & HIT_Y_MASK);
-        k3_groups_mark(s.D, y - x + moff);
-        k3_groups_mark(s.A, y + x);
+    {
+        int lmin = 0x7FFFFFFF, lmax = -1;
+        unsigned long long lsum = 0;
+        for (uint32_t i = tid; i < v.H; i += K3_THREADS) {
+            const uint2 h = v.hits[i];
+            const int x = (int)h.x, y = (int)(h.y & HIT_Y_MASK);
+            if (p0) { lmin = min(lmin, x); lmax = max(lmax, x); lsum += hit_mix(h.x, (uint32_t)y); }
+            k3_groups_mark(s.D, y - x + moff);
+            k3_groups_mark(s.A, y + x);
+        }
+        if (p0) k3_p0_reduce(sh, lmin, lmax, lsum);
     }
     __syncthreads();
+    if (p0) { p0->minx = sh.imin; p0->maxx = sh.imax; p0->cs = sh.u64a; }
     k3_groups_starts(s.D, W);
     k3_groups_starts(s.A, W);
     __syncthreads();
@@ -289,9 +319,9 @@ __device__ void k3_build_groups_both(const PlotView& v, K3Scratch& s, K3Shared& 
 // clean_dotdata_diagnal_and_anti_diagnal (Simple_function.pyx:432-448): keep a dot unless its y-x
 // chain group and its y+x chain group both have <= 10 members.  Returns count and sum |x-y| of the kept dots;
 // sets HIT_F_CLEAN on them when `write_flags` (the REDEF statistics read it back).
-__device__ void k3_clean_a6(const PlotView& v, K3Scratch& s, K3Shared& sh, PlotStat& st, bool write_flags) {
+__device__ void k3_clean_a6(const PlotView& v, K3Scratch& s, K3Shared& sh, PlotStat& st, bool write_flags, K3P0* p0) {
     const int moff = v.m - 1;
-    k3_build_groups_both(v, s, sh);
+    k3_build_groups_both(v, s, sh, p0);
     if (threadIdx.x == 0) { sh.u32a = 0; sh.u64a = 0; }
     __syncthreads();
     uint32_t lcnt = 0; unsigned long long lsum = 0;
@@ -321,14 +351,17 @@ __device__ __forceinline__ bool k3_a7_keep(uint32_t sz, uint32_t gmax) {
 
 // W10 cleaning (Simple_function.pyx:281-288): dis_cluster on y-x, then dis_cluster on y+x over the
 // dots the first step did not keep; union.  Returns count and the within-16% count.
-__device__ void k3_clean_w10(const PlotView& v, K3Scratch& s, K3Shared& sh, PlotStat& st) {
+__device__ void k3_clean_w10(const PlotView& v, K3Scratch& s, K3Shared& sh, PlotStat& st, K3P0* p0) {
     st.nclean = 0; st.cnt10 = 0;
-    if (v.H == 0) return;                               // uniform across the block
+    if (v.H == 0) {                                     // uniform across the block
+        if (p0) { p0->minx = 0x7FFFFFFF; p0->maxx = -1; p0->cs = 0; }
+        return;
+    }
     const int nb = v.n + v.m - 1;
     const int moff = v.m - 1;
     if (threadIdx.x == 0) { sh.u32a = 0; sh.u32b = 0; sh.u32c = 0; }
     k3_build_groups(v.hits, v.H, s.D, nb, sh, &K3Shared::gmaxD,
-                    [moff](const uint2& h) { return (int)(h.y & HIT_Y_MASK) - (int)h.x + moff; });
+                    [moff](const uint2& h) { return (int)(h.y & HIT_Y_MASK) - (int)h.x + moff; }, p0);
     const uint32_t gmax1 = sh.gmaxD;
     const K3Groups D = s.D;
     auto kept1 = [D, moff, gmax1](const uint2& h) {
@@ -556,37 +589,50 @@ __device__ void k3_eval(int mode, const PlotView* pv /*[2]: ref, alt*/, int len_
                         K3Scratch& s, K3Shared& sh, EvalResult& out, unsigned long long* cs /*[2]*/,
                         int* minx /*[2]*/, int* maxx /*[2]*/, bool have_pass0)
 {
-    if (!have_pass0) {                                 // spans + checksums; the caller hands them over when it has them
-        #pragma unroll 1
-        for (int w = 0; w < 2; ++w) k3_pass0(pv[w], sh, minx[w], maxx[w], cs[w]);
-    }
     out.a = 0; out.b = 0; out.valid = false;
     const double Hr = (double)pv[0].H, Ha = (double)pv[1].H;
     const double Lr = (double)len_ref, La = (double)len_alt;
-    const double span_r = (double)(maxx[0] - minx[0]) / Lr, span_a = (double)(maxx[1] - minx[1]) / La;
+    // What will be cleaned unless a span gate stops it follows from the hit counts alone (first steps of the ladders,
+    // Simple_function.pyx:187-190, 280-281, 244-246): the cleaning runs first, with pass 0 (spans + checksums; the caller hands
+    // them over when it has them) riding on its first pass over the hits, and the span gates are applied afterwards.  A task
+    // whose spans fail them was cleaned for nothing -- rare --, every other task reads its hits one time less.
+    bool want_a6 = false, want_w10 = false;
+    if (mode == 0) want_a6 = (pv[0].H > 2 && pv[1].H > 2) && (Hr / fmin(Lr, La) > 0.1);
+    else if (mode == 1) want_w10 = fmax(Hr / Lr, Ha / La) > 0.1;
+    else want_a6 = Hr / Lr > 0.1 && Ha / La > 0.1;
     PlotStat st[2] = {};
+    K3P0 p0[2];
+    const bool fuse = !have_pass0 && (want_a6 || want_w10);
+    if (!have_pass0 && !fuse) {
+        #pragma unroll 1
+        for (int w = 0; w < 2; ++w) k3_pass0(pv[w], sh, minx[w], maxx[w], cs[w]);
+    }
+    if (want_a6) {
+        #pragma unroll 1
+        for (int w = 0; w < 2; ++w) k3_clean_a6(pv[w], s, sh, st[w], mode == 2, fuse ? &p0[w] : nullptr);
+    } else if (want_w10) {
+        #pragma unroll 1
+        for (int w = 0; w < 2; ++w) k3_clean_w10(pv[w], s, sh, st[w], fuse ? &p0[w] : nullptr);
+    }
+    if (fuse) {
+        #pragma unroll 1
+        for (int w = 0; w < 2; ++w) { minx[w] = p0[w].minx; maxx[w] = p0[w].maxx; cs[w] = p0[w].cs; }
+    }
+    const double span_r = (double)(maxx[0] - minx[0]) / Lr, span_a = (double)(maxx[1] - minx[1]) / La;
     bool clean_a6 = false, clean_w10 = false;
     if (mode == 0) {                                   // ABS, Simple_function.pyx:187-203
-        if (!(pv[0].H > 2 && pv[1].H > 2)) return;
-        if (!(Hr / fmin(Lr, La) > 0.1)) return;
+        if (!want_a6) return;
         const bool rs = span_r > 0.6, as = span_a > 0.6;
         if (rs && as) clean_a6 = true;
         else if (rs) { out.a = 1.1; out.b = 2.1; }
         else if (as) { out.a = 2.1; out.b = 1.1; }
     } else if (mode == 1) {                            // W10, Simple_function.pyx:280-294
-        if (!(fmax(Hr / Lr, Ha / La) > 0.1)) return;
+        if (!want_w10) return;
         clean_w10 = true;
     } else {                                           // REDEF, Simple_function.pyx:244-257
-        if (!(Hr / Lr > 0.1 && Ha / La > 0.1)) return;
+        if (!want_a6) return;
         if (!(span_r > 0.7 && span_a > 0.7)) return;
         clean_a6 = true;
-    }
-    if (clean_a6) {
-        #pragma unroll 1
-        for (int w = 0; w < 2; ++w) k3_clean_a6(pv[w], s, sh, st[w], mode == 2);
-    } else if (clean_w10) {
-        #pragma unroll 1
-        for (int w = 0; w < 2; ++w) k3_clean_w10(pv[w], s, sh, st[w]);
     }
     if ((clean_a6 || clean_w10) && st[0].nclean > 0 && st[1].nclean > 0) {
         if (mode == 0) {

@@ -24,6 +24,8 @@
 //   * every pass body exists once (the four dots in flight rotate through one register pair) and the three stages
 //     have one call site each: with the bodies unrolled four times the kernel was 180 KB of code and instruction
 //     fetch was its first stall reason;
+//   * pass 0 (span of x, checksum) rides on the first cleaning pass: what to clean follows from the hit counts, the span
+//     gates are applied afterwards (a task whose spans fail them was cleaned for nothing -- rare);
 //   * tasks are pulled from a per-launch queue (one atomic per task), so warps never wait for the slowest
 //     task of a CTA.
 // Results are bit-identical to the CTA kernel's (all GPU tests and the soak run both through the oracle).
@@ -188,10 +190,13 @@ __device__ __forceinline__ void k3w_pass0(const PlotView& v, int lane, int& minx
 //   want10  the W10 cleaning (:281-288): dis_cluster on y-x, then dis_cluster on y+x over the dots the first step did not
 //           keep, union (-> nw, c10)
 // Both start from the chain groups of y-x over all dots, built once.
+// The first pass over the dots also does pass 0 (span of x, checksum): the caller decides what to clean from the hit
+// counts alone and applies the span gates afterwards, so a task's plots are read one time less.
 __device__ __forceinline__ void k3w_clean(const PlotView& v, const K3WSet& D, const K3WSet& A, int lane,
-                                          bool want6, bool want10, bool flags, K3WStat& st) {
+                                          bool want6, bool want10, bool flags, K3WStat& st,
+                                          int& minx, int& maxx, unsigned long long& csum) {
     st.n6 = 0; st.sumabs = 0; st.dmin = 0x7FFFFFFF; st.dmax = -0x7FFFFFFF; st.nw = 0; st.c10 = 0;
-    if (v.H == 0 || !(want6 || want10)) return;                     // warp-uniform
+    if (v.H == 0 || !(want6 || want10)) { k3w_pass0(v, lane, minx, maxx, csum); return; }   // warp-uniform
     const int nb = v.n + v.m - 1, moff = v.m - 1;
     const int W = (nb + 31) >> 5;
     const uint32_t H = v.H;
@@ -199,13 +204,22 @@ __device__ __forceinline__ void k3w_clean(const PlotView& v, const K3WSet& D, co
     k3w_clear(D.bits, W, lane);
     if (want6) k3w_clear(A.bits, W, lane);
     __syncwarp();
-    k3w_each(hits, H, lane, [&](const uint2& h, uint32_t, bool ok) {
-        if (ok) {
-            const int x = (int)h.x, y = (int)(h.y & HIT_Y_MASK);
-            k3w_mark(D.bits, y - x + moff);
-            if (want6) k3w_mark(A.bits, y + x);
-        }
-    });
+    {
+        int lmin = 0x7FFFFFFF, lmax = -1;
+        unsigned long long lsum = 0;
+        k3w_each(hits, H, lane, [&](const uint2& h, uint32_t, bool ok) {
+            if (ok) {
+                const int x = (int)h.x, y = (int)(h.y & HIT_Y_MASK);
+                lmin = min(lmin, x); lmax = max(lmax, x);
+                lsum += hit_mix(h.x, (uint32_t)y);
+                k3w_mark(D.bits, y - x + moff);
+                if (want6) k3w_mark(A.bits, y + x);
+            }
+        });
+        minx = __reduce_min_sync(K3W_FULL, lmin);
+        maxx = __reduce_max_sync(K3W_FULL, lmax);
+        csum = k3w_sum64(lsum);
+    }
     __syncwarp();
     const int ngD = k3w_starts(D, W, lane);
     const int ngA = want6 ? k3w_starts(A, W, lane) : 0;
@@ -395,6 +409,16 @@ __device__ __forceinline__ double k3w_redef_stat(const PlotView& v, uint32_t* au
     return cnt == 0 ? 0.0001 : fabs(((double)s64 * 0.5) / (double)cnt);
 }
 
+// The part of the gate ladders that needs only the hit counts: what an opinion WILL clean unless a span gate (which needs
+// pass 0) stops it.  Same expressions as in k3w_gates, so that plan.a6 / plan.w10 there imply the same here.
+__device__ __forceinline__ void k3w_hgates(int mode, uint32_t Hr_, uint32_t Ha_, int len_ref, int len_alt, bool& a6, bool& w10) {
+    const double Hr = (double)Hr_, Ha = (double)Ha_, Lr = (double)len_ref, La = (double)len_alt;
+    a6 = false; w10 = false;
+    if (mode == 0) a6 = (Hr_ > 2 && Ha_ > 2) && (Hr / fmin(Lr, La) > 0.1);
+    else if (mode == 1) w10 = fmax(Hr / Lr, Ha / La) > 0.1;
+    else a6 = Hr / Lr > 0.1 && Ha / La > 0.1;
+}
+
 struct K3WPlan {           // what the gates of one opinion ask for
     bool a6, w10;
     double a, b;           // the pair when the gates decide alone
@@ -468,23 +492,24 @@ k3w_score_reads(const K3Params p)
             const bool same = two && t.plot[2] == t.plot[0] && t.plot[3] == t.plot[1];
             int minx[4] = {0, 0, 0, 0}, maxx[4] = {0, 0, 0, 0};
             const int n_own = (two && !same) ? 4 : 2;               // plots this task looks at on their own
-            #pragma unroll 1
-            for (int e = 0; e < n_own; ++e) k3w_pass0(pv[e], lane, minx[e], maxx[e], cs[e]);
-            if (same) { minx[2] = minx[0]; maxx[2] = maxx[0]; minx[3] = minx[1]; maxx[3] = maxx[1]; cs[2] = cs[0]; cs[3] = cs[1]; }
             const int mode0 = two ? 0 : t.mode;
+            // what to clean follows from the hit counts; the span gates (pass 0, done inside the first cleaning pass) come after
+            bool h6, h10, hx, h10b = false;
+            k3w_hgates(mode0, pv[0].H, pv[1].H, t.len_ref, t.len_alt, h6, h10);
+            if (two) k3w_hgates(1, pv[2].H, pv[3].H, t.len_ref, t.len_alt, hx, h10b);
+            K3WStat sx[4];
+            const bool fused = same && h10b;                        // both opinions look at the same two plots: one cleaning call
+            #pragma unroll 1
+            for (int e = 0; e < n_own; ++e) {
+                const bool first = e < 2;
+                k3w_clean(pv[e], D, A, lane, first && h6, first ? (h10 || fused) : h10b, first && mode0 == 2, sx[e], minx[e], maxx[e], cs[e]);
+                __syncwarp();
+            }
+            if (same) { minx[2] = minx[0]; maxx[2] = maxx[0]; minx[3] = minx[1]; maxx[3] = maxx[1]; cs[2] = cs[0]; cs[3] = cs[1]; sx[2] = sx[0]; sx[3] = sx[1]; }
             const K3WPlan g0 = k3w_gates(mode0, pv[0].H, pv[1].H, t.len_ref, t.len_alt, minx[0], maxx[0], minx[1], maxx[1]);
             K3WPlan g1{false, false, 0.0, 0.0};
             if (two) g1 = k3w_gates(1, pv[2].H, pv[3].H, t.len_ref, t.len_alt, minx[2], maxx[2], minx[3], maxx[3]);
             ea = g0.a; eb = g0.b;
-            K3WStat sx[4];
-            const bool fused = same && g1.w10;                      // both opinions look at the same two plots: one cleaning call
-            #pragma unroll 1
-            for (int e = 0; e < n_own; ++e) {
-                const bool first = e < 2;
-                k3w_clean(pv[e], D, A, lane, first && g0.a6, first ? (g0.w10 || fused) : g1.w10, first && mode0 == 2, sx[e]);
-                __syncwarp();
-            }
-            if (same) { sx[2] = sx[0]; sx[3] = sx[1]; }
             const K3WStat* s0 = sx; const K3WStat* s1 = sx + 2;
             if (g0.a6 && s0[0].n6 > 0 && s0[1].n6 > 0) {
                 if (mode0 == 0) {
