@@ -365,3 +365,27 @@ def test_kernel3_variants_and_overlap_agree(engine):
         other.close()
     sample = w.batch.shard([1, 2, 3, 4, 50, 99, 140])
     _compare(engine.score(sample), BO.score_batch(sample))
+
+
+def test_short_range_plot_with_more_than_65535_dots(engine):
+    """A tandem repeat inside a SHORT window: the value range (n + m - 1 = 5 000 bins) puts the task in a class of the
+    warp-per-task kernel 3, whose group sizes are 16-bit counters, but the plot holds ~160 000 dots.  Such a plot overflows
+    its first-pass slab, and the re-scoring of its task must go to the CTA-per-task kernel (32-bit counters): results equal
+    the oracle in every mode."""
+    rng = np.random.default_rng(99)
+    b = Batch()
+    unit = synth.random_dna(rng, 11)
+    left, right = synth.random_dna(rng, 600), synth.random_dna(rng, 600)
+    ref = np.concatenate([left, np.tile(unit, 120), right])
+    alt = np.concatenate([left, np.tile(unit, 100), right])
+    rid, aid = b.add_seq(ref), b.add_seq(alt)
+    for j, mode in enumerate((MODE_ABS, MODE_W10, MODE_REDEF, MODE_ABS_AND_W10)):
+        read = np.concatenate([left[5 * j:], np.tile(unit, 118 + j), right])
+        b.add_task(b.add_seq(read), rid, aid, 0, 10, mode)
+    b.end_sv("repeat")
+    pb = b.pack()
+    exp = BO.score_batch(pb)
+    assert int(exp["task_hits"].max()) > 65535
+    got = engine.score(pb)
+    assert engine.timings()["n_overflow_plots"] > 0
+    _compare(got, exp)

@@ -833,8 +833,10 @@ int launch_k2_join(Handle* h, const JoinPlan& jp, size_t wi, K2JParams kp) {
 
 // kernel 3 over task ids [o0, o1) of scratch class c
 // `slot` = this launch's task-queue counter in d_k3q (zeroed by the caller)
-void launch_k3_class(Handle* h, K3Params kp, int c, int max_nb, size_t slot, cudaStream_t st) {
-    if (c < h->k3w_nclass && h->k3_mode == 1) {
+// `allow_warp` = false for the re-scored tasks of an overflowed wave: their plots hold more dots than n + m + 32 -- possibly more
+// than the 65 535 the warp kernel's 16-bit group sizes can count -- so they always go to the CTA-per-task kernel.
+void launch_k3_class(Handle* h, K3Params kp, int c, int max_nb, size_t slot, cudaStream_t st, bool allow_warp = true) {
+    if (c < h->k3w_nclass && h->k3_mode == 1 && allow_warp) {
         kp.nb_cap = k3_class_cap[c]; kp.use_global = 0; kp.gscratch = nullptr; kp.queue = h->d_k3q.p + slot;
         const size_t smem = (size_t)K3W_TEAMS * k3w_scratch_words(kp.nb_cap) * sizeof(uint32_t);
         const int per_sm = std::max(1, std::min(K3W_MINB, (int)((size_t)(226 * 1024) / (smem + 1024))));
@@ -970,7 +972,7 @@ int redo_wave(Handle* h, size_t wi, int64_t* launches) {
         kp.plots = d_re.p; kp.cnt = d_recnt.p; kp.op_status = h->d_op_status.p; kp.hits = h->d_ovf_hits.p;
         kp.task_score = h->d_task_score.p; kp.task_status = h->d_task_status.p; kp.task_stat = h->d_task_stat.p;
         kp.task_hits = h->d_task_hits.p; kp.task_hitsum = h->d_task_hitsum.p;
-        launch_k3_class(h, kp, c, std::max(re_max_nb, h->max_nb), h->waves.size() * K3_NCLASS + c, h->stream);
+        launch_k3_class(h, kp, c, std::max(re_max_nb, h->max_nb), h->waves.size() * K3_NCLASS + c, h->stream, /*allow_warp=*/false);
         ++*launches;
     }
     span_end(h, sp);

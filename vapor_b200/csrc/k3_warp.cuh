@@ -13,7 +13,8 @@
 //     instead of 6;
 //   * scratch per task is 0.78 bytes per bin instead of 1.95: the group-start bitmap overwrites the occupancy
 //     bitmap in place (the neighbour word travels by shuffle), word prefixes and group sizes are 16-bit (a plot of
-//     this class holds < 65 536 dots), the median histogram of REDEF reuses the group-size arrays;
+//     this class holds at most n + m + 32 < 65 536 dots in its first-pass slab; the tasks of plots that overflowed it
+//     are re-scored by the CTA kernel, api.cu launch_k3_class), the median histogram of REDEF reuses the group-size arrays;
 //   * the passes over a plot's dots are fused across the two opinions of the simple-DEL rule (ABS, then W10 on the
 //     same two plots, :1718-1726): both need the chain groups of y-x over all dots, built once -- 7 passes over the
 //     dots instead of 10;
