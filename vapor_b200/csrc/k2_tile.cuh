@@ -94,11 +94,33 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// Confirm a candidate on the code strings: structure k-mer == read k-mer, forward or reverse-complemented.
+// Four consecutive code bytes from any alignment: one or two aligned 32-bit loads + a funnel shift.  Reads up to 3 bytes
+// before p and 3 bytes past p + 3 (inside the code buffer: it starts 256-byte aligned and is allocated with 64 bytes of slack).
+__device__ __forceinline__ uint32_t k2_load4(const uint8_t* p) {
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
+    const uint32_t lo = q[0];
+    return a ? __funnelshift_r(lo, q[1], 8u * a) : lo;
+}
+
+// Confirm a candidate on the code strings: structure k-mer == read k-mer, forward or reverse-complemented -- four bases per
+// step (byte-wise compare of packed codes; the reverse complement is a byte reversal + invert_base on the four codes at once:
+// codes with bit 2 set (N, n, invalid) keep their value, the others flip their low two bits), the last k mod 4 bases one by one.
+// Every match of a hashed word (k > 15, or a k-mer holding N / lower case) comes through here.
 __device__ __noinline__ bool verify_kmer(const uint8_t* __restrict__ cr, const uint8_t* __restrict__ cs, int k) {
     bool fwd = true, rev = true;
-    for (int t = 0; t < k; ++t) {
-        int s = cs[t] & 15;
+    int t = 0;
+    for (; t + 4 <= k; t += 4) {
+        const uint32_t s = k2_load4(cs + t) & 0x0F0F0F0Fu;
+        const uint32_t r = k2_load4(cr + t) & 0x0F0F0F0Fu;
+        fwd &= (s == r);
+        uint32_t q = __byte_perm(k2_load4(cr + k - 4 - t) & 0x0F0F0F0Fu, 0u, 0x0123);    // bases k-1-t, k-2-t, k-3-t, k-4-t
+        q ^= 0x03030303u & ~(((q >> 2) & 0x01010101u) * 3u);
+        rev &= (s == q);
+        if (!(fwd | rev)) return false;
+    }
+    for (; t < k; ++t) {
+        const int s = cs[t] & 15;
         fwd &= (s == (cr[t] & 15));
         rev &= (s == comp_code(cr[k - 1 - t] & 15));
     }
